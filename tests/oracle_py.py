@@ -1,0 +1,203 @@
+"""ctypes bindings for the CPU oracle (oracle/_build/liboracle.so) and for the
+reference's own rect_remap() (oracle/_ref/libfpga_ref.so).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+REF_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libfpga_ref.so")
+
+# shipped rectification parameter set, src/StereoBM/src/fpga.c:190-226
+SHIPPED_RECT = dict(
+    f=[[40419817, 40382910], [39609530, 39627967]],
+    c=[320, 240],
+    f2inv=[6338213, 6338213],
+    c2_f2=[4984405, 5932596],
+    rot=[
+        [[16598538, -120818, 2439034], [137992, 16776300, -108069], [-2438123, 126979, 16598626]],
+        [[16569087, -69780, 2633522], [51223, 16776692, 122251], [-2633948, -112694, 16568783]],
+    ],
+)
+
+
+class RectParams(ctypes.Structure):
+    _fields_ = [("f", (ctypes.c_int32 * 2) * 2), ("c", ctypes.c_int32 * 2),
+                ("f2inv", ctypes.c_int32 * 2), ("c2_f2", ctypes.c_int32 * 2),
+                ("rot", ((ctypes.c_int32 * 3) * 3) * 2)]
+
+    @classmethod
+    def from_dict(cls, d):
+        p = cls()
+        for cam in range(2):
+            for k in range(2):
+                p.f[cam][k] = d["f"][cam][k]
+            for i in range(3):
+                for j in range(3):
+                    p.rot[cam][i][j] = d["rot"][cam][i][j]
+        for k in range(2):
+            p.c[k] = d["c"][k]; p.f2inv[k] = d["f2inv"][k]; p.c2_f2[k] = d["c2_f2"][k]
+        return p
+
+
+class BmRtlParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("wsz", "ndisp", "uni_enb", "uni_mode", "uni_thr", "x_store_offset", "rtl_extended", "bitserial_div")]
+
+
+class BmCvParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("wsz", "ndisp", "prefilter_cap", "texture_threshold", "uniqueness_ratio")]
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            build_oracle()
+        L = ctypes.CDLL(LIB_PATH)
+        self.L = L
+        u8p, i16p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int16)
+        L.orc_diven.restype = ctypes.c_uint64
+        L.orc_diven.argtypes = [ctypes.c_int] * 4 + [ctypes.c_uint64] * 2
+        L.orc_rect_remap.argtypes = [ctypes.POINTER(RectParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, i16p, i16p]
+        L.orc_rect_interp.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, i16p, i16p, u8p]
+        L.orc_xsobel_rtl.argtypes = [u8p, ctypes.c_int, ctypes.c_int, u8p]
+        L.orc_xsobel_cv.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p]
+        L.orc_bm_rtl.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(BmRtlParams), i16p]
+        L.orc_bm_rtl_last_sat_events.restype = ctypes.c_int64
+        L.orc_bm_cv.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(BmCvParams), i16p]
+        L.orc_reproject.argtypes = [i16p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
+                                    ctypes.POINTER(ctypes.c_float)]
+
+    def diven(self, DW, VW, QW, MSB_INV, dividend, divisor):
+        return int(self.L.orc_diven(DW, VW, QW, MSB_INV, dividend & (2**64 - 1), divisor & (2**64 - 1)))
+
+    def rect_remap(self, params, lr, W, H):
+        p = params if isinstance(params, RectParams) else RectParams.from_dict(params)
+        xs = np.empty((H, W), np.int16); ys = np.empty((H, W), np.int16)
+        i16p = ctypes.POINTER(ctypes.c_int16)
+        self.L.orc_rect_remap(ctypes.byref(p), lr, W, H, xs.ctypes.data_as(i16p), ys.ctypes.data_as(i16p))
+        return xs, ys
+
+    def rect_interp(self, src, xs, ys):
+        src, sp = _u8(src)
+        H, W = src.shape
+        xs = np.ascontiguousarray(xs, np.int16); ys = np.ascontiguousarray(ys, np.int16)
+        dst = np.empty((H, W), np.uint8)
+        i16p = ctypes.POINTER(ctypes.c_int16)
+        self.L.orc_rect_interp(sp, W, H, W, xs.ctypes.data_as(i16p), ys.ctypes.data_as(i16p),
+                               dst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return dst
+
+    def rectify(self, src, params, lr):
+        H, W = src.shape
+        xs, ys = self.rect_remap(params, lr, W, H)
+        return self.rect_interp(src, xs, ys)
+
+    def xsobel_rtl(self, src):
+        src, sp = _u8(src)
+        H, W = src.shape
+        dst = np.empty((H, W), np.uint8)
+        self.L.orc_xsobel_rtl(sp, W, H, dst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return dst
+
+    def xsobel_cv(self, src, cap=31):
+        src, sp = _u8(src)
+        H, W = src.shape
+        dst = np.empty((H, W), np.uint8)
+        self.L.orc_xsobel_cv(sp, W, H, cap, dst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return dst
+
+    def bm_rtl(self, xl, xr, wsz=21, ndisp=64, uni_enb=0, uni_mode=0, uni_thr=0,
+               x_store_offset=1, rtl_extended=0, bitserial_div=1):
+        xl, lp = _u8(xl); xr, rp = _u8(xr)
+        H, W = xl.shape
+        p = BmRtlParams(wsz, ndisp, uni_enb, uni_mode, uni_thr, x_store_offset, rtl_extended, bitserial_div)
+        disp = np.empty((H, W), np.int16)
+        rc = self.L.orc_bm_rtl(lp, rp, W, H, ctypes.byref(p), disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+        if rc != 0:
+            raise ValueError(f"orc_bm_rtl rc={rc}")
+        return disp
+
+    def sat_events(self):
+        return int(self.L.orc_bm_rtl_last_sat_events())
+
+    def bm_cv(self, pl, pr, wsz=21, ndisp=64, prefilter_cap=31, texture_threshold=10, uniqueness_ratio=10):
+        pl, lp = _u8(pl); pr, rp = _u8(pr)
+        H, W = pl.shape
+        p = BmCvParams(wsz, ndisp, prefilter_cap, texture_threshold, uniqueness_ratio)
+        disp = np.empty((H, W), np.int16)
+        rc = self.L.orc_bm_cv(lp, rp, W, H, ctypes.byref(p), disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+        if rc != 0:
+            raise ValueError(f"orc_bm_cv rc={rc}")
+        return disp
+
+    def reproject(self, disp, P_l, P_r, decim=1, apply_local=0):
+        disp = np.ascontiguousarray(disp, np.int16)
+        H, W = disp.shape
+        Pl = np.ascontiguousarray(P_l, np.float64).reshape(12); Pr = np.ascontiguousarray(P_r, np.float64).reshape(12)
+        out = np.empty((H // decim, W // decim, 3), np.float32)
+        dp = ctypes.POINTER(ctypes.c_double)
+        self.L.orc_reproject(disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), W, H, Pl.ctypes.data_as(dp),
+                             Pr.ctypes.data_as(dp), decim, apply_local, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        return out
+
+
+# ---- the reference's own rect_remap(), compiled from /root/reference into oracle/_ref ----
+class _RefRectParamCh(ctypes.Structure):      # struct RECT_PARAM_CH, fpga.h:250-256 (LP64 host layout)
+    _fields_ = [("f", ctypes.c_long * 2), ("c", ctypes.c_short * 2), ("f2inv", ctypes.c_long * 2),
+                ("c2_f2", ctypes.c_long * 2), ("rot", (ctypes.c_long * 3) * 3)]
+
+
+class _RefRectParam(ctypes.Structure):        # struct RECT_PARAM, fpga.h:258-260
+    _fields_ = [("ch", _RefRectParamCh * 2)]
+
+
+class _RefMat2S(ctypes.Structure):            # struct MAT2S, fpga.h:262-266
+    _fields_ = [("rows", ctypes.c_int), ("cols", ctypes.c_int), ("data", ctypes.POINTER(ctypes.c_short) * 2)]
+
+
+class RefFpga:
+    """The reference's fpga.c compiled unmodified (oracle/Makefile target `ref`)."""
+
+    def __init__(self):
+        self.L = ctypes.CDLL(REF_LIB_PATH)
+        self.L.rect_remap.argtypes = [ctypes.POINTER(_RefRectParam), ctypes.POINTER(_RefMat2S), ctypes.POINTER(_RefMat2S)]
+        self.L.rect_remap.restype = None
+
+    def rect_remap(self, d, W, H):
+        p = _RefRectParam()
+        for cam in range(2):
+            ch = p.ch[cam]
+            for k in range(2):
+                ch.f[k] = d["f"][cam][k]; ch.c[k] = d["c"][k]
+                ch.f2inv[k] = d["f2inv"][k]; ch.c2_f2[k] = d["c2_f2"][k]
+            for i in range(3):
+                for j in range(3):
+                    ch.rot[i][j] = d["rot"][cam][i][j]
+        maps, bufs = [], []
+        for _ in range(2):
+            m = _RefMat2S(); m.rows = H; m.cols = W
+            a = [np.zeros((H, W), np.int16) for _ in range(2)]
+            for k in range(2):
+                m.data[k] = a[k].ctypes.data_as(ctypes.POINTER(ctypes.c_short))
+            maps.append(m); bufs.append(a)
+        self.L.rect_remap(ctypes.byref(p), ctypes.byref(maps[0]), ctypes.byref(maps[1]))
+        return bufs
