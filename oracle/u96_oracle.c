@@ -67,7 +67,19 @@ static inline int64_t floordiv64(int64_t a, int64_t b)
 /* ------------------------------------------------------------------------ */
 /* rectification map: fpga.c:303-366 (== rect_rmp.v:366-585)                  */
 /* ------------------------------------------------------------------------ */
+void orc_rect_remap32(const orc_rect_params *p, int lr, int W, int H, int32_t *xs, int32_t *ys);
+
 void orc_rect_remap(const orc_rect_params *p, int lr, int W, int H, int16_t *xs, int16_t *ys)
+{
+    /* the reference stores the map as shorts (struct MAT2S, fpga.c:361-362) */
+    int32_t *x32 = (int32_t *)malloc(sizeof(int32_t) * (size_t)W * H), *y32 = (int32_t *)malloc(sizeof(int32_t) * (size_t)W * H);
+    orc_rect_remap32(p, lr, W, H, x32, y32);
+    for (int i = 0; i < W * H; i++) { xs[i] = (int16_t)x32[i]; ys[i] = (int16_t)y32[i]; }
+    free(x32); free(y32);
+}
+
+/* RTL-extended variant for frames beyond the RTL counter widths (W > 1023 or H > 511): no 16-bit wrap */
+void orc_rect_remap32(const orc_rect_params *p, int lr, int W, int H, int32_t *xs, int32_t *ys)
 {
     for (int y = 0; y < H; y++) {
         for (int x = 0; x < W; x++) {
@@ -84,15 +96,27 @@ void orc_rect_remap(const orc_rect_params *p, int lr, int W, int H, int16_t *xs,
             int64_t y2 = (ly * winv) >> 24;
             int64_t xf = ((x2 * p->f[lr][0]) >> 34) + ((int64_t)p->c[0] << 6);
             int64_t yf = ((y2 * p->f[lr][1]) >> 34) + ((int64_t)p->c[1] << 6);
-            xs[y * W + x] = (int16_t)((xf + 1) >> 1);
-            ys[y * W + x] = (int16_t)((yf + 1) >> 1);
+            xs[y * W + x] = (int32_t)((xf + 1) >> 1);
+            ys[y * W + x] = (int32_t)((yf + 1) >> 1);
         }
     }
 }
 
 /* rect_intp.v:288-412 */
+void orc_rect_interp32(const uint8_t *src, int W, int H, int src_stride,
+                       const int32_t *xs, const int32_t *ys, uint8_t *dst);
+
 void orc_rect_interp(const uint8_t *src, int W, int H, int src_stride,
                      const int16_t *xs, const int16_t *ys, uint8_t *dst)
+{
+    int32_t *x32 = (int32_t *)malloc(sizeof(int32_t) * (size_t)W * H), *y32 = (int32_t *)malloc(sizeof(int32_t) * (size_t)W * H);
+    for (int i = 0; i < W * H; i++) { x32[i] = xs[i]; y32[i] = ys[i]; }
+    orc_rect_interp32(src, W, H, src_stride, x32, y32, dst);
+    free(x32); free(y32);
+}
+
+void orc_rect_interp32(const uint8_t *src, int W, int H, int src_stride,
+                       const int32_t *xs, const int32_t *ys, uint8_t *dst)
 {
     for (int i = 0; i < W * H; i++) {
         int xi = xs[i] >> 5, xf = xs[i] & 31;
@@ -267,12 +291,17 @@ int orc_bm_rtl(const uint8_t *xl, const uint8_t *xr, int W, int H,
                 }
             }
             /* horizontal window: bm_calc_sad.v:501-605 */
+            uint32_t run[34];                         /* sliding add/sub, reset at line start (:571-587) */
+            for (int j = 0; j < 34; j++) {
+                run[j] = 0;
+                for (int k = 0; k < 2 * hwsz; k++) run[j] += col[(size_t)k * 34 + j];
+            }
             for (int xc = 0; xc < sad_wdt; xc++) {    /* centre column x = D + hwsz + xc */
                 uint16_t sad[34];
                 for (int j = 0; j < 34; j++) {
-                    uint32_t s = 0;
-                    for (int k = xc; k <= xc + 2 * hwsz; k++) s += col[(size_t)k * 34 + j];
-                    sad[j] = (uint16_t)(s > 0xFFFF ? 0xFFFF : s);   /* limit16 (unreachable) */
+                    run[j] += col[(size_t)(xc + 2 * hwsz) * 34 + j];
+                    if (xc > 0) run[j] -= col[(size_t)(xc - 1) * 34 + j];
+                    sad[j] = (uint16_t)(run[j] > 0xFFFF ? 0xFFFF : run[j]);   /* limit16 (unreachable) */
                 }
                 det_t dt = rtl_det(sad);
                 uint8_t fr = rtl_frac(dt.l, dt.min1, dt.r, p->bitserial_div);

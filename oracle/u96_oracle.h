@@ -45,6 +45,10 @@ uint64_t orc_diven(int DW, int VW, int QW, int MSB_INV, uint64_t dividend, uint6
 /* ---- rectification: fpga.c:303-366 == rect_rmp.v:366-585 ------------------ */
 /* Source coordinates (u10.5 / u9.5 fixed point) for every destination pixel. */
 void orc_rect_remap(const orc_rect_params *p, int lr, int W, int H, int16_t *xs, int16_t *ys);
+/* RTL-extended (no 16-bit wrap) variants for frames wider than 1023 or taller than 511 */
+void orc_rect_remap32(const orc_rect_params *p, int lr, int W, int H, int32_t *xs, int32_t *ys);
+void orc_rect_interp32(const uint8_t *src, int W, int H, int src_stride,
+                       const int32_t *xs, const int32_t *ys, uint8_t *dst);
 /* Bilinear interpolation with 5-bit fractions: rect_intp.v:288-412.
  * Out-of-image taps read 0 (the RTL leaves them undefined; build rule).       */
 void orc_rect_interp(const uint8_t *src, int W, int H, int src_stride,

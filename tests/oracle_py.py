@@ -77,6 +77,9 @@ class Oracle:
         L.orc_diven.argtypes = [ctypes.c_int] * 4 + [ctypes.c_uint64] * 2
         L.orc_rect_remap.argtypes = [ctypes.POINTER(RectParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, i16p, i16p]
         L.orc_rect_interp.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, i16p, i16p, u8p]
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        L.orc_rect_remap32.argtypes = [ctypes.POINTER(RectParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p, i32p]
+        L.orc_rect_interp32.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p, i32p, u8p]
         L.orc_xsobel_rtl.argtypes = [u8p, ctypes.c_int, ctypes.c_int, u8p]
         L.orc_xsobel_cv.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p]
         L.orc_bm_rtl.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(BmRtlParams), i16p]
@@ -106,8 +109,24 @@ class Oracle:
                                dst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
         return dst
 
-    def rectify(self, src, params, lr):
+    def rect_interp32(self, src, params, lr):
+        """RTL-extended rectification (32-bit coordinates, no short wrap)."""
+        src, sp = _u8(src)
         H, W = src.shape
+        p = params if isinstance(params, RectParams) else RectParams.from_dict(params)
+        xs = np.empty((H, W), np.int32); ys = np.empty((H, W), np.int32)
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        self.L.orc_rect_remap32(ctypes.byref(p), lr, W, H, xs.ctypes.data_as(i32p), ys.ctypes.data_as(i32p))
+        dst = np.empty((H, W), np.uint8)
+        self.L.orc_rect_interp32(sp, W, H, W, xs.ctypes.data_as(i32p), ys.ctypes.data_as(i32p),
+                                 dst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return dst
+
+    def rectify(self, src, params, lr):
+        """Reference semantics (short map) inside the RTL counter widths, RTL-extended beyond."""
+        H, W = src.shape
+        if W > 1023 or H > 511:
+            return self.rect_interp32(src, params, lr)
         xs, ys = self.rect_remap(params, lr, W, H)
         return self.rect_interp(src, xs, ys)
 

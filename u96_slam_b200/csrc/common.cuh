@@ -1,0 +1,47 @@
+// common.cuh -- shared declarations for the libu96stereo kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/u96_stereo.h"
+
+namespace u96 {
+
+// Device image: n frames back to back, row pitch in bytes (multiple of 128).
+struct Img8 {
+    uint8_t *p;
+    int pitch;           // bytes per row
+    size_t frame;        // bytes per frame (pitch * H)
+};
+struct Img16 {
+    int16_t *p;
+    int pitch;           // elements per row
+    size_t frame;        // elements per frame
+};
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// ---- stage launchers (each returns the number of kernels it launched) ----
+struct RectMapParams { u96_rect_params p; int W, H; int wrap16; };
+
+int launch_rect_build_map(const RectMapParams &rp, int2 *map /*[2][H][W]*/, cudaStream_t s);
+int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
+                      Img8 dstL, Img8 dstR, const int2 *map, int W, int H, int n, cudaStream_t s);
+int launch_xsobel(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
+                  Img8 dstL, Img8 dstR, int W, int H, int n, int profile, int cap, cudaStream_t s);
+
+struct BmConfig {
+    int W, H, D, wsz, profile;
+    int uni_enable, uni_mode, uni_thr, x_store_offset, rtl_extended;   // RTL
+    int cap, tex_thr, uniq;                                            // OPENCV
+};
+int  bm_smem_bytes(const BmConfig &c);
+int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
+              const BmConfig &c, int n, cudaStream_t s);
+
+int launch_reproject(const int16_t *disp, int dpitch, size_t dframe, int W, int H, int n,
+                     const double *P_l, const double *P_r, int decim, int flags, float *xyz, cudaStream_t s);
+
+int run_microbench(int which, double *gops);
+
+}  // namespace u96

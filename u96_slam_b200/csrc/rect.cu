@@ -1,0 +1,123 @@
+// rect.cu -- stereo rectification for sm_100a.
+//
+//   k_rect_build_map : the fixed-point inverse map of StereoBM/src/fpga.c:303-366
+//                      (== dvp/rtl/rect_rmp.v:366-585), run once per parameter set.
+//   k_rect_remap     : 5-bit-fraction bilinear gather of dvp/rtl/rect_intp.v:288-412.
+//
+// The map is frame-invariant, so it is materialised once (8 B/px/camera, L2-resident)
+// and the per-frame kernel is a pure gather: 1 B/px read + 1 B/px written to HBM.
+// The FPGA's run-length command stream (fpga.c:368-605) is a line-buffer scheduling
+// artefact and has no GPU counterpart: every destination pixel is written exactly once.
+#include "common.cuh"
+
+namespace u96 {
+
+struct RectConst {
+    long long f[2][2], rot[2][3][3];
+    long long c[2], f2inv[2], c2_f2[2];
+};
+
+__global__ void __launch_bounds__(256) k_rect_build_map(RectConst k, int2 *__restrict__ map, int W, int H, int wrap16)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int lr = blockIdx.z;
+    if (x >= W) return;
+    // (u10.0)*(u-8.32) -> (u1.24), minus (u0.24)                         fpga.c:317-323
+    const long long xd = (((long long)x * k.f2inv[0]) >> 8) - k.c2_f2[0];
+    const long long yd = (((long long)y * k.f2inv[1]) >> 8) - k.c2_f2[1];
+    // each product truncated separately, then summed                     fpga.c:325-340
+    const long long lx = ((k.rot[lr][0][0] * xd) >> 24) + ((k.rot[lr][1][0] * yd) >> 24) + k.rot[lr][2][0];
+    const long long ly = ((k.rot[lr][0][1] * xd) >> 24) + ((k.rot[lr][1][1] * yd) >> 24) + k.rot[lr][2][1];
+    const long long lw = ((k.rot[lr][0][2] * xd) >> 24) + ((k.rot[lr][1][2] * yd) >> 24) + k.rot[lr][2][2];
+    // (1ull << 48) / lw is an unsigned 64-bit division in the reference   fpga.c:343
+    const long long winv = (long long)((1ull << 48) / (unsigned long long)lw);
+    const long long x2 = (lx * winv) >> 24;
+    const long long y2 = (ly * winv) >> 24;
+    const long long xf = ((x2 * k.f[lr][0]) >> 34) + (k.c[0] << 6);
+    const long long yf = ((y2 * k.f[lr][1]) >> 34) + (k.c[1] << 6);
+    long long xs = (xf + 1) >> 1, ys = (yf + 1) >> 1;
+    if (wrap16) { xs = (short)xs; ys = (short)ys; }     // MAT2S stores shorts (fpga.c:361-362)
+    else {                                               // RTL-extended: saturate far outside
+        xs = max(-64ll, min(xs, (long long)(W + 1) * 32));
+        ys = max(-64ll, min(ys, (long long)(H + 1) * 32));
+    }
+    map[((size_t)lr * H + y) * W + x] = make_int2((int)xs, (int)ys);
+}
+
+int launch_rect_build_map(const RectMapParams &rp, int2 *map, cudaStream_t s)
+{
+    RectConst k;
+    for (int cam = 0; cam < 2; cam++) {
+        for (int i = 0; i < 2; i++) k.f[cam][i] = rp.p.f[cam][i];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) k.rot[cam][i][j] = rp.p.rot[cam][i][j];
+    }
+    for (int i = 0; i < 2; i++) { k.c[i] = rp.p.c[i]; k.f2inv[i] = rp.p.f2inv[i]; k.c2_f2[i] = rp.p.c2_f2[i]; }
+    dim3 grid((rp.W + 255) / 256, rp.H, 2);
+    k_rect_build_map<<<grid, 256, 0, s>>>(k, map, rp.W, rp.H, rp.wrap16);
+    return 1;
+}
+
+// One thread = 4 consecutive destination pixels of one row of one camera; it keeps the
+// 4 map entries and bilinear weights in registers and loops over FPB frames of the batch,
+// so the map is read once per FPB frames.  Taps outside the source read 0.
+constexpr int RECT_FPB = 8;
+
+__global__ void __launch_bounds__(128) k_rect_remap(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR,
+                                                    int sp, size_t sf, uint8_t *__restrict__ dL, uint8_t *__restrict__ dR,
+                                                    int dp, size_t df, const int2 *__restrict__ map, int W, int H, int n)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    const int lr = blockIdx.z & 1;
+    const int f0 = (blockIdx.z >> 1) * RECT_FPB;
+    if (x4 >= W) return;
+    const int2 *m = map + ((size_t)lr * H + y) * W + x4;
+    int off[4];          // byte offset of the upper-left tap (may be outside)
+    uint32_t w01[4], w23[4];   // packed weights: w00 | w01<<16, w10 | w11<<16   (u1.10 each)
+    uint32_t ok[4];      // validity bits of the four taps
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int2 e = (x4 + k < W) ? m[k] : make_int2(-64, -64);
+        const int xi = e.x >> 5, xf = e.x & 31, yi = e.y >> 5, yf = e.y & 31;
+        w01[k] = (uint32_t)((32 - xf) * (32 - yf)) | ((uint32_t)(xf * (32 - yf)) << 16);
+        w23[k] = (uint32_t)((32 - xf) * yf) | ((uint32_t)(xf * yf) << 16);
+        const bool x0 = (xi >= 0 && xi < W), x1 = (xi + 1 >= 0 && xi + 1 < W);
+        const bool y0 = (yi >= 0 && yi < H), y1 = (yi + 1 >= 0 && yi + 1 < H);
+        ok[k] = (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 2u : 0u) | (x0 && y1 ? 4u : 0u) | (x1 && y1 ? 8u : 0u);
+        off[k] = yi * sp + xi;
+    }
+    const uint8_t *src = (lr ? srcR : srcL) + (size_t)f0 * sf;
+    uint8_t *dst = (lr ? dR : dL) + (size_t)f0 * df + (size_t)y * dp + x4;
+    const int nf = min(RECT_FPB, n - f0);
+    for (int f = 0; f < nf; f++) {
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint8_t *t = src + off[k];
+            const uint32_t ul = (ok[k] & 1u) ? __ldg(t) : 0u;
+            const uint32_t ur = (ok[k] & 2u) ? __ldg(t + 1) : 0u;
+            const uint32_t dl = (ok[k] & 4u) ? __ldg(t + sp) : 0u;
+            const uint32_t dr = (ok[k] & 8u) ? __ldg(t + sp + 1) : 0u;
+            // u8 * u1.10 summed -> u8.10 ; ((s>>9)+1)>>1 with clamp      rect_intp.v:347-405
+            const uint32_t s = ul * (w01[k] & 0xFFFFu) + ur * (w01[k] >> 16) + dl * (w23[k] & 0xFFFFu) + dr * (w23[k] >> 16);
+            const uint32_t r = min(255u, ((s >> 9) + 1u) >> 1);
+            out |= r << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(dst) = out;      // pitch is a multiple of 128: always in-row
+        src += sf;
+        dst += df;
+    }
+}
+
+int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
+                      Img8 dstL, Img8 dstR, const int2 *map, int W, int H, int n, cudaStream_t s)
+{
+    const int tx = 128;
+    dim3 grid((W / 4 + 1 + tx - 1) / tx, H, 2 * ((n + RECT_FPB - 1) / RECT_FPB));
+    k_rect_remap<<<grid, tx, 0, s>>>(srcL, srcR, src_pitch, src_frame, dstL.p, dstR.p, dstL.pitch, dstL.frame, map, W, H, n);
+    return 1;
+}
+
+}  // namespace u96

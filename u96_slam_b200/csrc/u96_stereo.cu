@@ -1,0 +1,456 @@
+// u96_stereo.cu -- the C ABI of libu96stereo (include/u96_stereo.h): handle, banks, streams.
+//
+// The handle plays the role of the reference's `class Fpga` (slam/include/core/FPGA.h:347-397,
+// slam/src/core/FPGA.cpp): it owns two banks (A/B) of every buffer the FPGA keeps in DDR
+// (RECT, XSBL, DISP; StereoBM/src/fpga.h:50-68), fills a bank asynchronously on submit and copies
+// results out on receive.  There is no CPU code path: every stage is a CUDA kernel.
+#include <deque>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+
+using namespace u96;
+
+static thread_local std::string g_cuda_err;
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            g_cuda_err = std::string(#call) + ": " + cudaGetErrorString(e__);             \
+            return U96_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+namespace {
+
+enum { FROM_RAW = 0, FROM_RECT = 1, FROM_XSBL = 2 };
+
+struct Bank {
+    uint8_t *raw[2] = {nullptr, nullptr}, *rect[2] = {nullptr, nullptr}, *xsbl[2] = {nullptr, nullptr};
+    int16_t *disp = nullptr;
+    // where the current contents of each stage live (internal buffer or a caller's device pointer)
+    const uint8_t *cur_raw[2] = {nullptr, nullptr}, *cur_rect[2] = {nullptr, nullptr}, *cur_xsbl[2] = {nullptr, nullptr};
+    int raw_pitch = 0, rect_pitch = 0, xsbl_pitch = 0;
+    size_t raw_frame = 0, rect_frame = 0, xsbl_frame = 0;
+    int n = 0, from = -1;
+    bool filled = false, pending = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr, ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace
+
+struct u96_handle {
+    int device = 0, maxW = 0, maxH = 0, maxB = 0;
+    int pitch = 0;                 // internal u8 row pitch (bytes)
+    u96_bm_params bm{};
+    u96_rect_params rect{};
+    bool rect_set = false, map_valid = false;
+    int2 *map = nullptr;
+    Bank bank[2];
+    std::deque<int> fifo;
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false, profiling = false;
+    int64_t launches = 0;
+    float *xyz = nullptr;
+    size_t xyz_cap = 0;
+};
+
+static int validate_bm(const u96_handle *h, const u96_bm_params &p)
+{
+    if (p.width <= 0 || p.height <= 0 || p.width > h->maxW || p.height > h->maxH) return U96_ERR_INVALID;
+    if (p.min_disparity != 0) return U96_ERR_UNSUPPORTED;
+    if (!(p.block_size & 1) || p.block_size < 3 || p.block_size > 31) return U96_ERR_INVALID;
+    const int hw = p.block_size >> 1;
+    int max_ad;
+    if (p.profile == U96_PROFILE_RTL) {
+        // bm.v:174-177: wsz 5 bit, ndisp 9 bit; processed in 32-disparity dphases (bm_ibuf.v:143-189)
+        if (p.num_disparities < 32 || p.num_disparities > 256 || (p.num_disparities & 31)) return U96_ERR_INVALID;
+        if (p.uni_thr < 0 || p.uni_thr > 1023) return U96_ERR_INVALID;
+        if (p.x_store_offset != 0 && p.x_store_offset != 1) return U96_ERR_INVALID;
+        if (p.width - p.num_disparities - 1 - 2 * hw <= 0) return U96_ERR_INVALID;
+        max_ad = 63;
+    } else if (p.profile == U96_PROFILE_OPENCV) {
+        if (p.block_size < 5) return U96_ERR_INVALID;
+        if (p.num_disparities < 16 || p.num_disparities > 256 || (p.num_disparities & 15)) return U96_ERR_INVALID;
+        if (p.prefilter_cap < 1 || p.prefilter_cap > 63) return U96_ERR_INVALID;
+        if (p.uniqueness_ratio < 0 || p.texture_threshold < 0) return U96_ERR_INVALID;
+        if (p.width - p.num_disparities + 1 - 2 * hw <= 0) return U96_ERR_INVALID;
+        max_ad = 2 * p.prefilter_cap;
+    } else return U96_ERR_INVALID;
+    if (p.height - 2 * hw <= 0) return U96_ERR_INVALID;
+    if (p.block_size * p.block_size * max_ad > 65535) return U96_ERR_UNSUPPORTED;     // window sums are u16
+    BmConfig c{p.width, p.height, p.num_disparities, p.block_size, p.profile, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (bm_smem_bytes(c) > 227 * 1024) return U96_ERR_UNSUPPORTED;
+    return U96_OK;
+}
+
+static BmConfig bm_config(const u96_bm_params &p)
+{
+    BmConfig c;
+    c.W = p.width; c.H = p.height; c.D = p.num_disparities; c.wsz = p.block_size; c.profile = p.profile;
+    c.uni_enable = p.uni_enable; c.uni_mode = p.uni_mode; c.uni_thr = p.uni_thr;
+    c.x_store_offset = p.x_store_offset; c.rtl_extended = p.rtl_extended;
+    c.cap = p.prefilter_cap; c.tex_thr = p.texture_threshold; c.uniq = p.uniqueness_ratio;
+    return c;
+}
+
+extern "C" {
+
+int u96_abi_version(void) { return U96_ABI_VERSION; }
+
+const char *u96_strerror(int code)
+{
+    switch (code) {
+    case U96_OK: return "ok";
+    case U96_ERR_INVALID: return "invalid argument";
+    case U96_ERR_CUDA: return "CUDA error";
+    case U96_ERR_NOMEM: return "out of memory";
+    case U96_ERR_STATE: return "bank not ready / wrong state";
+    case U96_ERR_UNSUPPORTED: return "unsupported parameter combination";
+    case U96_ERR_NODEVICE: return "no CUDA device (there is no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+const char *u96_last_cuda_error(void) { return g_cuda_err.c_str(); }
+
+int u96_create(u96_handle **out, int device, int max_w, int max_h, int max_batch)
+{
+    if (!out || max_w <= 0 || max_h <= 0 || max_batch <= 0) return U96_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { g_cuda_err = "no CUDA device"; return U96_ERR_NODEVICE; }
+    if (device < 0 || device >= ndev) return U96_ERR_INVALID;
+    CK(cudaSetDevice(device));
+    u96_handle *h = new (std::nothrow) u96_handle();
+    if (!h) return U96_ERR_NOMEM;
+    h->device = device; h->maxW = max_w; h->maxH = max_h; h->maxB = max_batch;
+    h->pitch = align_up(max_w, 128);
+    const size_t img = (size_t)h->pitch * max_h * max_batch;
+    auto fail = [&](int rc) { u96_destroy(h); return rc; };
+    for (int b = 0; b < 2; b++) {
+        Bank &k = h->bank[b];
+        for (int i = 0; i < 2; i++) {
+            if (cudaMalloc(&k.raw[i], img) != cudaSuccess || cudaMalloc(&k.rect[i], img) != cudaSuccess ||
+                cudaMalloc(&k.xsbl[i], img) != cudaSuccess) return fail(U96_ERR_NOMEM);
+        }
+        if (cudaMalloc(&k.disp, img * sizeof(int16_t)) != cudaSuccess) return fail(U96_ERR_NOMEM);
+        if (cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking) != cudaSuccess) return fail(U96_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming) != cudaSuccess) return fail(U96_ERR_CUDA);
+        for (int i = 0; i < 5; i++)
+            if (cudaEventCreate(&k.ev[i]) != cudaSuccess) return fail(U96_ERR_CUDA);
+    }
+    if (cudaMalloc(&h->map, sizeof(int2) * 2 * (size_t)max_w * max_h) != cudaSuccess) return fail(U96_ERR_NOMEM);
+    // defaults = what the firmware programs (fpga.c:150-160): 640x480, wsz 21, 64 disparities, uniqueness off
+    u96_bm_params d{};
+    d.width = max_w; d.height = max_h; d.block_size = 21; d.num_disparities = 64; d.prefilter_cap = 31;
+    d.uniqueness_ratio = 10; d.texture_threshold = 10; d.profile = U96_PROFILE_RTL; d.x_store_offset = 1;
+    h->bm = d;
+    *out = h;
+    return U96_OK;
+}
+
+void u96_destroy(u96_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (int b = 0; b < 2; b++) {
+        Bank &k = h->bank[b];
+        if (k.stream) cudaStreamSynchronize(k.stream);
+        for (int i = 0; i < 2; i++) { cudaFree(k.raw[i]); cudaFree(k.rect[i]); cudaFree(k.xsbl[i]); }
+        cudaFree(k.disp);
+        if (k.done) cudaEventDestroy(k.done);
+        for (int i = 0; i < 5; i++) if (k.ev[i]) cudaEventDestroy(k.ev[i]);
+        if (k.stream) cudaStreamDestroy(k.stream);
+    }
+    cudaFree(h->map);
+    cudaFree(h->xyz);
+    delete h;
+}
+
+int u96_set_bm_params(u96_handle *h, const u96_bm_params *p)
+{
+    if (!h || !p) return U96_ERR_INVALID;
+    const int rc = validate_bm(h, *p);
+    if (rc != U96_OK) return rc;
+    if (p->width != h->bm.width || p->height != h->bm.height) h->map_valid = false;
+    h->bm = *p;
+    return U96_OK;
+}
+
+int u96_set_bm_registers(u96_handle *h, uint32_t image_size, uint32_t bm_setting, uint32_t uni_filt_ctrl)
+{
+    if (!h) return U96_ERR_INVALID;
+    u96_bm_params p = h->bm;
+    p.profile = U96_PROFILE_RTL;
+    p.height = (image_size >> 16) & 0x1FF;            // bm.v:170-171
+    p.width = image_size & 0x3FF;
+    p.block_size = (bm_setting >> 16) & 0x1F;         // bm.v:174-177
+    p.num_disparities = bm_setting & 0x1FF;
+    p.uni_enable = (uni_filt_ctrl >> 31) & 1;         // bm.v:183-187
+    p.uni_mode = (uni_filt_ctrl >> 16) & 1;
+    p.uni_thr = uni_filt_ctrl & 0x3FF;
+    p.min_disparity = 0;
+    return u96_set_bm_params(h, &p);
+}
+
+int u96_get_bm_params(u96_handle *h, u96_bm_params *p)
+{
+    if (!h || !p) return U96_ERR_INVALID;
+    *p = h->bm;
+    return U96_OK;
+}
+
+int u96_set_rect_params(u96_handle *h, const u96_rect_params *p)
+{
+    if (!h || !p) return U96_ERR_INVALID;
+    h->rect = *p;
+    h->rect_set = true;
+    h->map_valid = false;
+    return U96_OK;
+}
+
+int u96_set_stream(u96_handle *h, void *cuda_stream)
+{
+    if (!h) return U96_ERR_INVALID;
+    h->user_stream = (cudaStream_t)cuda_stream;
+    h->use_user_stream = true;
+    return U96_OK;
+}
+
+int u96_set_profiling(u96_handle *h, int on)
+{
+    if (!h) return U96_ERR_INVALID;
+    h->profiling = on != 0;
+    return U96_OK;
+}
+
+int64_t u96_kernel_launches(u96_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+static cudaStream_t bank_stream(u96_handle *h, int bank) { return h->use_user_stream ? h->user_stream : h->bank[bank].stream; }
+
+static int ensure_map(u96_handle *h, cudaStream_t s)
+{
+    if (h->map_valid) return U96_OK;
+    if (!h->rect_set) return U96_ERR_STATE;
+    RectMapParams rp;
+    rp.p = h->rect; rp.W = h->bm.width; rp.H = h->bm.height;
+    rp.wrap16 = (rp.W <= 1023 && rp.H <= 511) ? 1 : 0;      // RTL counter widths; beyond = RTL-extended
+    h->launches += launch_rect_build_map(rp, h->map, s);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));                             // other bank's stream may use the map next
+    h->map_valid = true;
+    return U96_OK;
+}
+
+// device_src: pointers are device memory; try zero-copy
+static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, const uint8_t *R, int stride, int n, bool device_src)
+{
+    if (!h || !L || !R || bank < 0 || bank > 1 || n <= 0 || n > h->maxB) return U96_ERR_INVALID;
+    const int W = h->bm.width, H = h->bm.height;
+    if (stride < W) return U96_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    Bank &k = h->bank[bank];
+    if (k.pending) return U96_ERR_STATE;                      // bank still in flight: wait() first
+    cudaStream_t s = bank_stream(h, bank);
+    const int pitch = h->pitch;
+    const size_t frame = (size_t)pitch * H;
+    if (from == FROM_RAW) { const int rc = ensure_map(h, s); if (rc != U96_OK) return rc; }
+    if (h->profiling) CK(cudaEventRecord(k.ev[0], s));
+
+    uint8_t *dstbuf[2];
+    for (int i = 0; i < 2; i++) dstbuf[i] = (from == FROM_RAW) ? k.raw[i] : (from == FROM_RECT) ? k.rect[i] : k.xsbl[i];
+    const uint8_t *src[2] = {L, R};
+    const uint8_t *cur[2];
+    int cur_pitch; size_t cur_frame;
+    const bool zero_copy = device_src && (stride % 16 == 0) && (stride >= align_up(W, 16)) &&
+                           (((uintptr_t)L | (uintptr_t)R) % 16 == 0);
+    if (zero_copy) {
+        cur[0] = L; cur[1] = R; cur_pitch = stride; cur_frame = (size_t)stride * H;
+    } else {
+        for (int i = 0; i < 2; i++)
+            CK(cudaMemcpy2DAsync(dstbuf[i], pitch, src[i], stride, W, (size_t)H * n,
+                                 device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        cur[0] = dstbuf[0]; cur[1] = dstbuf[1]; cur_pitch = pitch; cur_frame = frame;
+    }
+    if (h->profiling) CK(cudaEventRecord(k.ev[1], s));
+
+    const Img8 rectL{k.rect[0], pitch, frame}, rectR{k.rect[1], pitch, frame};
+    const Img8 xsblL{k.xsbl[0], pitch, frame}, xsblR{k.xsbl[1], pitch, frame};
+    const Img16 disp{k.disp, pitch, frame};
+    if (from == FROM_RAW) {
+        k.cur_raw[0] = cur[0]; k.cur_raw[1] = cur[1]; k.raw_pitch = cur_pitch; k.raw_frame = cur_frame;
+        h->launches += launch_rect_remap(cur[0], cur[1], cur_pitch, cur_frame, rectL, rectR, h->map, W, H, n, s);
+        k.cur_rect[0] = k.rect[0]; k.cur_rect[1] = k.rect[1]; k.rect_pitch = pitch; k.rect_frame = frame;
+    } else if (from == FROM_RECT) {
+        k.cur_rect[0] = cur[0]; k.cur_rect[1] = cur[1]; k.rect_pitch = cur_pitch; k.rect_frame = cur_frame;
+    }
+    if (h->profiling) CK(cudaEventRecord(k.ev[2], s));
+    if (from <= FROM_RECT) {
+        h->launches += launch_xsobel(k.cur_rect[0], k.cur_rect[1], k.rect_pitch, k.rect_frame, xsblL, xsblR, W, H, n,
+                                     h->bm.profile, h->bm.prefilter_cap, s);
+        k.cur_xsbl[0] = k.xsbl[0]; k.cur_xsbl[1] = k.xsbl[1]; k.xsbl_pitch = pitch; k.xsbl_frame = frame;
+    } else {
+        k.cur_xsbl[0] = cur[0]; k.cur_xsbl[1] = cur[1]; k.xsbl_pitch = cur_pitch; k.xsbl_frame = cur_frame;
+    }
+    if (h->profiling) CK(cudaEventRecord(k.ev[3], s));
+    h->launches += launch_bm(k.cur_xsbl[0], k.cur_xsbl[1], k.xsbl_pitch, k.xsbl_frame, disp, bm_config(h->bm), n, s);
+    if (h->profiling) CK(cudaEventRecord(k.ev[4], s));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(k.done, s));
+    k.n = n; k.from = from; k.filled = true; k.pending = true;
+    h->fifo.push_back(bank);
+    return U96_OK;
+}
+
+static int receive_u8(u96_handle *h, int bank, const uint8_t *const cur[2], int pitch, size_t frame, int min_from,
+                      uint8_t *L, uint8_t *R)
+{
+    if (!h || bank < 0 || bank > 1 || !L || !R) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!k.filled || k.from > min_from) return U96_ERR_STATE;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    const int W = h->bm.width, H = h->bm.height;
+    (void)frame;
+    uint8_t *dst[2] = {L, R};
+    for (int i = 0; i < 2; i++)
+        CK(cudaMemcpy2DAsync(dst[i], W, cur[i], pitch, W, (size_t)H * k.n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return U96_OK;
+}
+
+extern "C" {
+
+int u96_submit_raw(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n)
+{ return submit_common(h, bank, FROM_RAW, L, R, stride, n, false); }
+int u96_submit_rect(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n)
+{ return submit_common(h, bank, FROM_RECT, L, R, stride, n, false); }
+int u96_submit_xsbl(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n)
+{ return submit_common(h, bank, FROM_XSBL, L, R, stride, n, false); }
+int u96_submit_raw_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n)
+{ return submit_common(h, bank, FROM_RAW, (const uint8_t *)dL, (const uint8_t *)dR, stride, n, true); }
+int u96_submit_rect_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n)
+{ return submit_common(h, bank, FROM_RECT, (const uint8_t *)dL, (const uint8_t *)dR, stride, n, true); }
+int u96_submit_xsbl_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n)
+{ return submit_common(h, bank, FROM_XSBL, (const uint8_t *)dL, (const uint8_t *)dR, stride, n, true); }
+
+int u96_wait(u96_handle *h, int *active_bank)
+{
+    if (!h) return U96_ERR_INVALID;
+    if (h->fifo.empty()) return U96_ERR_STATE;
+    const int b = h->fifo.front();
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->bank[b].done));
+    h->fifo.pop_front();
+    h->bank[b].pending = false;
+    if (active_bank) *active_bank = b;
+    return U96_OK;
+}
+
+int u96_receive_rect(u96_handle *h, int bank, uint8_t *L, uint8_t *R)
+{
+    if (!h || bank < 0 || bank > 1) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    return receive_u8(h, bank, k.cur_rect, k.rect_pitch, k.rect_frame, FROM_RECT, L, R);
+}
+
+int u96_receive_xsbl(u96_handle *h, int bank, uint8_t *L, uint8_t *R)
+{
+    if (!h || bank < 0 || bank > 1) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    return receive_u8(h, bank, k.cur_xsbl, k.xsbl_pitch, k.xsbl_frame, FROM_XSBL, L, R);
+}
+
+int u96_receive_disp(u96_handle *h, int bank, int16_t *disp)
+{
+    if (!h || bank < 0 || bank > 1 || !disp) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!k.filled) return U96_ERR_STATE;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    const int W = h->bm.width, H = h->bm.height;
+    CK(cudaMemcpy2DAsync(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
+                         cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return U96_OK;
+}
+
+int u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_r[12], int decim, int flags, float *xyz)
+{
+    if (!h || bank < 0 || bank > 1 || !P_l || !P_r || !xyz) return U96_ERR_INVALID;
+    if (decim != 1 && decim != 2 && decim != 4 && decim != 8) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!k.filled) return U96_ERR_STATE;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    const int W = h->bm.width, H = h->bm.height;
+    const size_t count = (size_t)(W / decim) * (H / decim) * k.n * 3;
+    if (count > h->xyz_cap) {
+        cudaFree(h->xyz); h->xyz = nullptr; h->xyz_cap = 0;
+        if (cudaMalloc(&h->xyz, count * sizeof(float)) != cudaSuccess) return U96_ERR_NOMEM;
+        h->xyz_cap = count;
+    }
+    h->launches += launch_reproject(k.disp, h->pitch, (size_t)h->pitch * H, W, H, k.n, P_l, P_r, decim, flags, h->xyz, s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(xyz, h->xyz, count * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return U96_OK;
+}
+
+int u96_bank_device_ptr(u96_handle *h, int bank, int which, void **dptr, int *pitch_bytes, size_t *frame_bytes)
+{
+    if (!h || bank < 0 || bank > 1 || !dptr || which < 0 || which >= U96_BUF_COUNT) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    const int H = h->bm.height;
+    const void *p = nullptr; int pitch = h->pitch; size_t frame = (size_t)h->pitch * H;
+    switch (which) {
+    case U96_BUF_RAW_L: case U96_BUF_RAW_R: p = k.raw[which - U96_BUF_RAW_L]; break;
+    case U96_BUF_RECT_L: case U96_BUF_RECT_R: p = k.rect[which - U96_BUF_RECT_L]; break;
+    case U96_BUF_XSBL_L: case U96_BUF_XSBL_R: p = k.xsbl[which - U96_BUF_XSBL_L]; break;
+    case U96_BUF_DISP: p = k.disp; pitch *= 2; frame *= 2; break;
+    }
+    *dptr = const_cast<void *>(p);
+    if (pitch_bytes) *pitch_bytes = pitch;
+    if (frame_bytes) *frame_bytes = frame;
+    return U96_OK;
+}
+
+int u96_host_alloc(void **p, size_t bytes)
+{
+    if (!p) return U96_ERR_INVALID;
+    CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return U96_OK;
+}
+
+int u96_host_free(void *p)
+{
+    CK(cudaFreeHost(p));
+    return U96_OK;
+}
+
+int u96_last_stage_ms(u96_handle *h, int bank, float ms[4])
+{
+    if (!h || bank < 0 || bank > 1 || !ms) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!h->profiling || !k.filled || k.pending) return U96_ERR_STATE;
+    for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms[i], k.ev[i], k.ev[i + 1]));
+    return U96_OK;
+}
+
+int u96_microbench(int device, int which, double *gops)
+{
+    if (!gops) return U96_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return U96_ERR_NODEVICE;
+    CK(cudaSetDevice(device));
+    return run_microbench(which, gops);
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// xsobel.cu -- x-Sobel prefilter with clipping, sm_100a.
+//
+//   RTL profile    : dvp/rtl/xsbl2.v:185-198 (limit), :682-698 (horizontal difference),
+//                    :826-857 (vertical 1-2-1), :861-874 (column borders).
+//                    out = clip(s,-32,31)+32 ; cols 0,W-1 = 32 ; rows 0,H-1 = 0 (never written,
+//                    firmware memsets the bank to 0: StereoBM/src/fpga.c:113-114).
+//   OPENCV profile : cv::StereoBM prefilterXSobel as called from slam/src/core/main.cpp:197-217
+//                    out = clip(s,-cap,cap)+cap ; cols = cap ; rows reflect-101 ; odd H: last row = cap.
+//
+// HBM-bound: 1 B/px read + 1 B/px written.  One thread produces 16 output pixels with one
+// 16-byte store; the three input rows are fetched as 16-byte vectors (L1/L2 absorb the 3x reuse).
+// The arithmetic is 2x16-bit packed: vertical 1-2-1 on widened bytes, horizontal difference with a
+// bias that keeps both halves non-negative, clamp with VIMNMX.U16x2.
+#include "common.cuh"
+
+namespace u96 {
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+
+// v = a + 2b + c for 4 bytes -> two u16x2 registers (px0,px1) (px2,px3)
+__device__ __forceinline__ void vsum4(uint32_t a, uint32_t b, uint32_t c, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t al = prmt(a, 0, 0x4140), ah = prmt(a, 0, 0x4342);
+    const uint32_t bl = prmt(b, 0, 0x4140), bh = prmt(b, 0, 0x4342);
+    const uint32_t cl = prmt(c, 0, 0x4140), ch = prmt(c, 0, 0x4342);
+    lo = al + 2u * bl + cl;       // max 4*255 = 1020 per half: no carry between halves
+    hi = ah + 2u * bh + ch;
+}
+
+template <int PROFILE>
+__global__ void __launch_bounds__(128) k_xsobel(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR, int sp, size_t sf,
+                                                uint8_t *__restrict__ dL, uint8_t *__restrict__ dR, int dp, size_t df,
+                                                int W, int H, int cap)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y;
+    const int lr = blockIdx.z & 1, f = blockIdx.z >> 1;
+    if (x0 >= W) return;
+    const uint8_t *src = (lr ? srcR : srcL) + (size_t)f * sf;
+    uint8_t *dst = (lr ? dR : dL) + (size_t)f * df + (size_t)y * dp + x0;
+
+    int ym, yp;
+    uint32_t border, lo_off, hi_lim;     // clamp to [lo_off, hi_lim] after adding the bias
+    if (PROFILE == U96_PROFILE_RTL) {
+        if (y == 0 || y == H - 1) {      // invalid lines
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+            return;
+        }
+        ym = y - 1; yp = y + 1;
+        border = 32;
+    } else {
+        if ((H & 1) && y == H - 1) {
+            const uint32_t c4 = (uint32_t)cap * 0x01010101u;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(c4, c4, c4, c4);
+            return;
+        }
+        ym = (y > 0) ? y - 1 : 1;        // reflect-101
+        yp = (y < H - 1) ? y + 1 : H - 2;
+        border = (uint32_t)cap;
+    }
+    // s + BIAS, BIAS = 1024 + off keeps both halves positive (|s| <= 1020)
+    const uint32_t off = (PROFILE == U96_PROFILE_RTL) ? 32u : (uint32_t)cap;
+    const uint32_t bias = (1024u + off) * 0x00010001u;
+    lo_off = 1024u * 0x00010001u;                                       // value 0 after clamp
+    hi_lim = (1024u + ((PROFILE == U96_PROFILE_RTL) ? 63u : 2u * (uint32_t)cap)) * 0x00010001u;
+
+    const uint8_t *ra = src + (size_t)ym * sp + x0, *rb = src + (size_t)y * sp + x0, *rc = src + (size_t)yp * sp + x0;
+    const uint4 a = *reinterpret_cast<const uint4 *>(ra), b = *reinterpret_cast<const uint4 *>(rb), c = *reinterpret_cast<const uint4 *>(rc);
+    // neighbours left of x0 and right of x0+15 (clamped addresses; the border columns are overwritten below)
+    const int xl = (x0 > 0) ? -1 : 0, xr = (x0 + 16 < W) ? 16 : 15;
+    const uint32_t vl = (uint32_t)ra[xl] + 2u * rb[xl] + rc[xl];
+    const uint32_t vr = (uint32_t)ra[xr] + 2u * rb[xr] + rc[xr];
+
+    uint32_t v[10];      // v[0] = (-, px-1) ; v[1..8] = pairs (px0,px1)...(px14,px15) ; v[9] = (px16, -)
+    v[0] = vl << 16;
+    vsum4(a.x, b.x, c.x, v[1], v[2]);
+    vsum4(a.y, b.y, c.y, v[3], v[4]);
+    vsum4(a.z, b.z, c.z, v[5], v[6]);
+    vsum4(a.w, b.w, c.w, v[7], v[8]);
+    v[9] = vr;
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t r2[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = 1 + 2 * q + k;                           // pair (x, x+1)
+            const uint32_t nxt = prmt(v[i], v[i + 1], 0x5432);     // (x+1, x+2)
+            const uint32_t prv = prmt(v[i - 1], v[i], 0x5432);     // (x-1, x)
+            uint32_t t = nxt + bias - prv;                         // s + off + 1024 per half, no borrow
+            t = __vmaxu2(t, lo_off);
+            t = __vminu2(t, hi_lim);
+            r2[k] = t;
+        }
+        o[q] = prmt(r2[0], r2[1], 0x6420);                        // low bytes: 1024 = 0x400 drops out
+    }
+    // column borders                                              xsbl2.v:869-872
+    if (x0 == 0) o[0] = (o[0] & 0xFFFFFF00u) | border;
+    if (x0 + 16 >= W) {
+        const int k = W - 1 - x0;                                  // 0..15
+        o[k >> 2] = (o[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (border << (8 * (k & 3)));
+    }
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int launch_xsobel(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
+                  Img8 dstL, Img8 dstR, int W, int H, int n, int profile, int cap, cudaStream_t s)
+{
+    const int tx = 128;
+    dim3 grid((align_up(W, 16) / 16 + tx - 1) / tx, H, 2 * n);
+    if (profile == U96_PROFILE_RTL)
+        k_xsobel<U96_PROFILE_RTL><<<grid, tx, 0, s>>>(srcL, srcR, src_pitch, src_frame, dstL.p, dstR.p, dstL.pitch, dstL.frame, W, H, cap);
+    else
+        k_xsobel<U96_PROFILE_OPENCV><<<grid, tx, 0, s>>>(srcL, srcR, src_pitch, src_frame, dstL.p, dstR.p, dstL.pitch, dstL.frame, W, H, cap);
+    return 1;
+}
+
+}  // namespace u96
