@@ -1,0 +1,163 @@
+"""CPU tests: the oracle against every pin the reference offers -- no GPU needed."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle_py import SHIPPED_RECT, REF_LIB_PATH
+
+
+def test_kat1_xsobel_matches_reference_golden(oracle, golden):
+    # data/ref_rect_{l,r} -> data/ref_xsbl_{l,r}: the only golden pair the reference ships (xsbl2.v)
+    for side in "lr":
+        got = oracle.xsobel_rtl(golden["rect_" + side])
+        assert np.array_equal(got, golden["xsbl_" + side])
+    assert golden["xsbl_l"][0].max() == 0 and golden["xsbl_l"][-1].max() == 0      # invalid lines stay 0
+    assert (golden["xsbl_l"][1:-1, 0] == 32).all() and (golden["xsbl_l"][1:-1, -1] == 32).all()
+
+
+def test_opencv_prefilter_differs_from_rtl(oracle, golden):
+    # cap-31 rule mismatches the RTL goldens on most pixels
+    cv = oracle.xsobel_cv(golden["rect_l"], 31)
+    assert (cv != golden["xsbl_l"]).mean() > 0.5
+
+
+def test_rect_remap_matches_reference_function(oracle):
+    # fixture = output of the reference's own rect_remap() (fpga.c:303-366) compiled into oracle/_ref
+    m = np.load(os.path.join(os.path.dirname(__file__), "golden", "rect_remap_ref.npz"))
+    for lr, n in ((0, "l"), (1, "r")):
+        xs, ys = oracle.rect_remap(SHIPPED_RECT, lr, 640, 480)
+        assert np.array_equal(xs, m["xs_" + n]) and np.array_equal(ys, m["ys_" + n])
+    # shipped parameters map inside the source image
+    assert xs.min() >= 0 and xs.max() < 640 * 32 and ys.min() >= 0 and ys.max() < 480 * 32
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIB_PATH), reason="oracle/_ref not built (no /root/reference here)")
+def test_rect_remap_live_reference_random_params(oracle):
+    from oracle_py import RefFpga
+    ref = RefFpga()
+    rng = np.random.default_rng(7)
+    for _ in range(3):
+        d = {k: (np.array(v) + rng.integers(-2000, 2000, np.array(v).shape)).tolist() for k, v in SHIPPED_RECT.items()}
+        d["c"] = [320, 240]
+        d["f2inv"] = [d["f2inv"][0]] * 2 if False else d["f2inv"]
+        # the reference C code reads f2inv/c2_f2/c per channel, the RTL shares channel 0's: feed identical values
+        got = [oracle.rect_remap(d, lr, 160, 120) for lr in (0, 1)]
+        want = ref.rect_remap(d, 160, 120)
+        for lr in (0, 1):
+            assert np.array_equal(got[lr][0], want[lr][0]) and np.array_equal(got[lr][1], want[lr][1])
+
+
+def test_rect_interp_identity_and_clamp(oracle):
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, (24, 40), dtype=np.uint8)
+    ys, xs = np.meshgrid(np.arange(24) * 32, np.arange(40) * 32, indexing="ij")
+    assert np.array_equal(oracle.rect_interp(src, xs, ys), src)                  # integer coordinates: identity
+    out = oracle.rect_interp(src, xs + 16, ys)                                   # half-pixel: rounded mean
+    want = ((src[:, :-1].astype(int) * 16 * 32 + src[:, 1:].astype(int) * 16 * 32 >> 9) + 1) >> 1
+    assert np.array_equal(out[:, :-1], want)
+    assert (oracle.rect_interp(src, xs - 64, ys) [:, :1] == 0).all()             # outside taps read 0
+
+
+def test_kat3_diven_closed_forms(oracle):
+    rng = np.random.default_rng(3)
+    # rect: diven#(26,26,26,24)(2^24, lw) == floor(2^48/lw)
+    for lw in rng.integers(1 << 22, 1 << 25, 3000):
+        assert oracle.diven(26, 26, 26, 24, 1 << 24, int(lw)) == ((1 << 48) // int(lw)) & ((1 << 26) - 1)
+    # sub-pixel: diven#(18,18,8,17)(n, d) == floor(128 n / d) for d > 0, |n| <= d/2, n of either sign.
+    # (bm_calc_frac.v:80-95: a negative divisor implies neg_val, i.e. dividend 0 -- checked below;
+    #  for n != 0 with d < 0 the non-restoring divider is NOT floor, but that input cannot occur.)
+    for _ in range(20000):
+        d = int(rng.integers(1, 1 << 16)) * 2
+        n = int(rng.integers(-(d // 2), d // 2 + 1))
+        q = oracle.diven(18, 18, 8, 17, n & 0x3FFFF, d & 0x3FFFF)
+        assert q == ((128 * n) // d) & 0xFF, (n, d, q)
+    # 0 / +-d -> 0
+    for d in (2, -2, 500, -131070):
+        assert oracle.diven(18, 18, 8, 17, 0, d & 0x3FFFF) == 0
+    # uniqueness: diven#(17,17,11,16)(a, b) == floor(1024 a / b) (a <= b), b == 0 -> 2047
+    for _ in range(20000):
+        b = int(rng.integers(1, 1 << 16)); a = int(rng.integers(0, b + 1))
+        assert oracle.diven(17, 17, 11, 16, a, b) == (1024 * a // b) & 0x7FF
+    # min2 == 0 implies min1 == 0 (min1 <= min2 always): the only reachable zero-divisor case
+    assert oracle.diven(17, 17, 11, 16, 0, 0) == 2047
+    assert oracle.diven(17, 17, 11, 16, 77, 77) == 1024          # equal minima: & 0x3FF -> 0 -> passes the filter
+
+
+# CRCs of an independent numpy reading of the RTL (non-authoritative cross-check)
+@pytest.mark.parametrize("wsz,uni,thr,valid,total,crc", [
+    (21, 0, 0, 253088, 194655560, 0x3C312D26),
+    (21, 1, 921, 157291, 133771940, 0xF3284A7C),
+    (15, 0, 0, 259128, 190344441, 0xD0650EA3),
+])
+def test_bm_rtl_cross_check_with_survey(oracle, golden, wsz, uni, thr, valid, total, crc):
+    d = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=wsz, ndisp=64, uni_enb=uni, uni_thr=thr)
+    assert int((d >= 0).sum()) == valid and int(d.astype(np.int64).sum()) == total
+    assert zlib.crc32(d.tobytes()) & 0xFFFFFFFF == crc
+    # closed-form divisions == bit-serial diven on real data
+    d2 = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=wsz, ndisp=64, uni_enb=uni, uni_thr=thr, bitserial_div=0)
+    assert np.array_equal(d, d2)
+
+
+def test_bm_rtl_saturation_facts(oracle, golden):
+    # 10-bit column-sum saturation happens on ref_xsbl at wsz 21, never at wsz <= 16
+    oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=64)
+    assert oracle.sat_events() > 0
+    oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=15, ndisp=64)
+    assert oracle.sat_events() == 0
+
+
+def test_bm_rtl_layout(oracle, golden):
+    d = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=64, x_store_offset=1)
+    assert (d[:10] == -1).all() and (d[-10:] == -1).all()            # hwsz invalid rows top/bottom
+    assert (d[:, :64 + 10 + 1] == -1).all() and (d[:, -10:] == -1).all()   # ndisp+hwsz+1 leading, hwsz trailing
+    d0 = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=64, x_store_offset=0)
+    assert np.array_equal(d0[:, :-1], d[:, 1:])                      # A1: same values one column to the left
+    assert d.max() < 64 * 16 + 8
+
+
+def test_bm_cv_matches_cv2_golden(oracle, golden, cv_golden):
+    pl, pr = oracle.xsobel_cv(golden["rect_l"], 31), oracle.xsobel_cv(golden["rect_r"], 31)
+    for k, want in cv_golden.items():
+        if not k.startswith("D"):
+            continue
+        D, B, T, U = [int(s[1:]) for s in k.split("_")]
+        got = oracle.bm_cv(pl, pr, wsz=B, ndisp=D, texture_threshold=T, uniqueness_ratio=U)
+        assert got.dtype == np.int16 and np.array_equal(got, want), k
+    assert (cv_golden["D64_B21_T10_U10"] == -16).any()               # KAT-4: invalid = -16
+
+
+def test_bm_cv_matches_live_cv2_on_synthetic(oracle):
+    cv2 = pytest.importorskip("cv2")
+    import u96_slam_b200 as u
+    L, R = u.synth_pair(2, 5, 320, 120, 48)
+    for D, B, T, U in ((48, 9, 10, 15), (32, 15, 0, 0)):
+        bm = cv2.StereoBM_create(D, B)
+        bm.setPreFilterCap(25); bm.setTextureThreshold(T); bm.setUniquenessRatio(U)
+        bm.setSpeckleWindowSize(0); bm.setDisp12MaxDiff(-1); bm.setMinDisparity(0)
+        want = bm.compute(L, R)
+        got = oracle.bm_cv(oracle.xsobel_cv(L, 25), oracle.xsobel_cv(R, 25), wsz=B, ndisp=D, prefilter_cap=25,
+                           texture_threshold=T, uniqueness_ratio=U)
+        assert np.array_equal(got, want)
+
+
+def test_reproject_matches_float_formula(oracle):
+    rng = np.random.default_rng(5)
+    disp = rng.integers(-16, 64 * 16, (48, 64)).astype(np.int16)
+    P_l = np.array([[718.856 * 640 / 1241, 0, 607.19 * 640 / 1241, 0], [0, 718.856 * 480 / 376, 185.22 * 480 / 376, 0], [0, 0, 1, 0]])
+    P_r = P_l.copy(); P_r[0, 3] = -386.1448 * 640 / 1241
+    for decim in (1, 4):
+        out = oracle.reproject(disp, P_l, P_r, decim, 0)
+        d = disp[::decim, ::decim].astype(np.float32) / np.float32(16)
+        bad = d <= 0
+        assert np.isnan(out[bad]).all()
+        c = np.float32(P_r[0, 2] - P_l[0, 2])
+        dc = (d + c).astype(np.float32)
+        Wx = ((P_l[0, 3] / P_l[0, 0] - P_r[0, 3] / P_r[0, 0]) / dc.astype(np.float64)).astype(np.float32)
+        Z = (P_l[0, 0] * Wx.astype(np.float64)).astype(np.float32)
+        u0 = (np.arange(out.shape[1]) * decim).astype(np.float32)[None, :]
+        X = ((u0.astype(np.float64) - P_l[0, 2]) * Wx.astype(np.float64)).astype(np.float32)
+        assert np.array_equal(out[..., 2][~bad], Z[~bad]) and np.array_equal(out[..., 0][~bad], X[~bad])
+        loc = oracle.reproject(disp, P_l, P_r, decim, 1)
+        assert np.array_equal(loc[..., 0][~bad], out[..., 2][~bad]) and np.array_equal(loc[..., 1][~bad], -out[..., 0][~bad])
