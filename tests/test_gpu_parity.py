@@ -1,0 +1,235 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every stage through the C ABI, bit-exact against
+the CPU oracle, the reference's golden vectors and the committed cv2 fixtures."""
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def u(libpath):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import u96_slam_b200
+    return u96_slam_b200
+
+
+@pytest.fixture(scope="module")
+def fe640(u):
+    fe = u.StereoFrontEnd(0, 640, 480, 4)
+    yield fe
+    fe.close()
+
+
+def run_xsbl(fe, bank, xl, xr, **params):
+    fe.set_bm_params(**params)
+    fe.submit_xsbl(bank, xl, xr)
+    assert fe.wait() == bank
+    return fe.receive_disp(bank)
+
+
+RTL = dict(width=640, height=480, profile=0, num_disparities=64, block_size=21, uni_enable=0, uni_mode=0, uni_thr=0,
+           x_store_offset=1, rtl_extended=0, min_disparity=0)
+
+
+def test_c1_xsobel_matches_reference_golden(u, fe640, golden):
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)       # Fpga_Init values, fpga.c:150-160
+    fe640.submit_rect(0, golden["rect_l"], golden["rect_r"])
+    b = fe640.wait()
+    sl, sr = fe640.receive_xsbl(b)
+    assert np.array_equal(sl[0], golden["xsbl_l"]) and np.array_equal(sr[0], golden["xsbl_r"])
+    rl, rr = fe640.receive_rect(b)                                   # copy-out of the bank (receiveRectImages)
+    assert np.array_equal(rl[0], golden["rect_l"]) and np.array_equal(rr[0], golden["rect_r"])
+
+
+@pytest.mark.parametrize("wsz,uni,thr,mode,crc", [
+    (21, 0, 0, 0, 0x3C312D26), (21, 1, 921, 0, 0xF3284A7C), (15, 0, 0, 0, 0xD0650EA3),
+    (9, 1, 800, 1, None), (5, 0, 0, 0, None), (17, 0, 0, 0, None), (31, 0, 0, 0, None), (3, 0, 0, 0, None)])
+def test_c1_bm_rtl_bundled_pair(u, fe640, golden, oracle, wsz, uni, thr, mode, crc):
+    d = run_xsbl(fe640, 1, golden["xsbl_l"], golden["xsbl_r"], **dict(RTL, block_size=wsz, uni_enable=uni, uni_thr=thr, uni_mode=mode))[0]
+    want = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=wsz, ndisp=64, uni_enb=uni, uni_thr=thr, uni_mode=mode)
+    assert np.array_equal(d, want), int((d != want).sum())
+    if crc is not None:                                              # SURVEY Appendix B cross-check values
+        assert zlib.crc32(d.tobytes()) & 0xFFFFFFFF == crc
+
+
+@pytest.mark.parametrize("D", [32, 96, 128, 256])
+def test_bm_rtl_disparity_ranges(u, fe640, golden, oracle, D):
+    ext = int(D > 128)
+    d = run_xsbl(fe640, 0, golden["xsbl_l"], golden["xsbl_r"], **dict(RTL, num_disparities=D, rtl_extended=ext))[0]
+    assert np.array_equal(d, oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=D, rtl_extended=ext))
+
+
+def test_bm_rtl_x_store_offset_and_sign_extension(u, fe640, golden, oracle):
+    xl, xr = golden["xsbl_l"], golden["xsbl_r"]
+    d0 = run_xsbl(fe640, 0, xl, xr, **dict(RTL, x_store_offset=0))[0]
+    assert np.array_equal(d0, oracle.bm_rtl(xl, xr, wsz=21, ndisp=64, x_store_offset=0))
+    # D=256 without the extension reproduces the RTL's bit-15 sign extension (bm_obuf2.v:153)
+    d = run_xsbl(fe640, 1, xl, xr, **dict(RTL, num_disparities=256, rtl_extended=0))[0]
+    assert np.array_equal(d, oracle.bm_rtl(xl, xr, wsz=21, ndisp=256, rtl_extended=0))
+
+
+def test_opencv_profile_matches_cv2_golden(u, fe640, golden, cv_golden, oracle):
+    for k, want in cv_golden.items():
+        if not k.startswith("D"):
+            continue
+        D, B, T, U = [int(s[1:]) for s in k.split("_")]
+        fe640.set_bm_params(width=640, height=480, profile=u.PROFILE_OPENCV, num_disparities=D, block_size=B,
+                            texture_threshold=T, uniqueness_ratio=U, prefilter_cap=31, min_disparity=0)
+        fe640.submit_rect(0, golden["rect_l"], golden["rect_r"])
+        b = fe640.wait()
+        pl, pr = fe640.receive_xsbl(b)
+        assert np.array_equal(pl[0], oracle.xsobel_cv(golden["rect_l"], 31))
+        assert np.array_equal(fe640.receive_disp(b)[0], want), k
+
+
+def test_stereobm_facade_matches_live_cv2(u):
+    cv2 = pytest.importorskip("cv2")
+    L, R = u.synth_pair(2, 3, 400, 200, 48)
+    ref = cv2.StereoBM_create(48, 11)
+    ref.setPreFilterCap(20); ref.setTextureThreshold(5); ref.setUniquenessRatio(12)
+    ref.setSpeckleWindowSize(0); ref.setDisp12MaxDiff(-1)
+    bm = u.StereoBM.create(48, 11)
+    bm.setPreFilterCap(20); bm.setTextureThreshold(5); bm.setUniquenessRatio(12)
+    assert np.array_equal(bm.compute(L, R), ref.compute(L, R))
+
+
+def test_c2_raw_pipeline_batch_and_banks(u, fe640, oracle):
+    L, R = u.synth_batch(1, 0, 4, 640, 480, 64)
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    fe640.set_bm_params(x_store_offset=1)
+    fe640.set_rect_params(u.SHIPPED_RECT_PARAMS)
+    fe640.submit_raw(0, L[:3], R[:3])                # two banks in flight, FIFO order
+    fe640.submit_raw(1, L[3:], R[3:])
+    assert fe640.wait() == 0 and fe640.wait() == 1
+    out = {0: (fe640.receive_rect(0), fe640.receive_xsbl(0), fe640.receive_disp(0)),
+           1: (fe640.receive_rect(1), fe640.receive_xsbl(1), fe640.receive_disp(1))}
+    for i in range(4):
+        bank, j = (0, i) if i < 3 else (1, 0)
+        (gl, gr), (sl, sr), d = out[bank]
+        wl, wr = oracle.rectify(L[i], u.SHIPPED_RECT_PARAMS, 0), oracle.rectify(R[i], u.SHIPPED_RECT_PARAMS, 1)
+        assert np.array_equal(gl[j], wl) and np.array_equal(gr[j], wr)
+        wxl, wxr = oracle.xsobel_rtl(wl), oracle.xsobel_rtl(wr)
+        assert np.array_equal(sl[j], wxl) and np.array_equal(sr[j], wxr)
+        assert np.array_equal(d[j], oracle.bm_rtl(wxl, wxr, wsz=21, ndisp=64))
+
+
+def test_fpga_facade_file_mode(u, golden, oracle):
+    """FPGA_TEST call stack (main.cpp:165-181): setRectImage -> SW_START -> receiveData."""
+    f = u.Fpga()
+    assert f.registerOpen() == 0 and f.memoryOpen() == 0
+    for it in range(3):
+        bank = it % 2
+        f.setRectImage(bank, golden["rect_l"], golden["rect_r"])
+        f.start(bank)
+        active, rl, rr, disp = f.receiveData()
+        assert active == bank and disp.dtype == np.int16 and disp.shape == (480, 640)
+        assert np.array_equal(disp, oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=64))
+    assert f.registerClose() == 0
+
+
+@pytest.mark.parametrize("B", [9, 15, 21])
+def test_c3_kitti_shape_both_profiles(u, oracle, B):
+    W, H, D = 1242, 375, 128
+    L, R = u.synth_batch(2, 0, 2, W, H, D)
+    rp = u.identity_rect_params(W, H, 700.0)
+    with u.StereoFrontEnd(0, W, H, 2) as fe:
+        fe.set_rect_params(rp)
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=B, num_disparities=D, x_store_offset=1)
+        fe.submit_raw(0, L, R); b = fe.wait()
+        gl, gr = fe.receive_rect(b); d = fe.receive_disp(b)
+        wl, wr = oracle.rectify(L[1], rp, 0), oracle.rectify(R[1], rp, 1)
+        assert np.array_equal(gl[1], wl) and np.array_equal(gr[1], wr)
+        assert np.array_equal(d[1], oracle.bm_rtl(oracle.xsobel_rtl(wl), oracle.xsobel_rtl(wr), wsz=B, ndisp=D))
+        fe.set_bm_params(profile=u.PROFILE_OPENCV, texture_threshold=10, uniqueness_ratio=10, prefilter_cap=31)
+        fe.submit_rect(1, L, R); b = fe.wait()
+        assert np.array_equal(fe.receive_disp(b)[0], oracle.bm_cv(oracle.xsobel_cv(L[0]), oracle.xsobel_cv(R[0]), wsz=B, ndisp=D))
+
+
+def test_c4_full_hd_256_disparities(u, oracle):
+    W, H, D = 1920, 1080, 256
+    L, R = u.synth_batch(3, 0, 2, W, H, D)
+    with u.StereoFrontEnd(0, W, H, 2) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=21, num_disparities=D, rtl_extended=1, x_store_offset=1)
+        fe.submit_rect(0, L, R); b = fe.wait()
+        d = fe.receive_disp(b)
+        want = oracle.bm_rtl(oracle.xsobel_rtl(L[1]), oracle.xsobel_rtl(R[1]), wsz=21, ndisp=D, rtl_extended=1)
+        assert np.array_equal(d[1], want)
+        # size-independent properties at full size: borders invalid, range, idempotence, batch == single
+        assert (d[:, :10] == -1).all() and (d[:, :, :D + 11] == -1).all() and d.max() < D * 16 + 8
+        fe.submit_rect(1, L[1:], R[1:]); b = fe.wait()
+        assert np.array_equal(fe.receive_disp(b)[0], d[1])
+
+
+def test_property_uniform_shift_of_right_image(u, fe640, oracle):
+    """Shifting R right by k columns lowers every interior disparity by exactly k (x16)."""
+    L, R = u.synth_pair(1, 7, 640, 480, 64)
+    xl, xr = oracle.xsobel_rtl(L), oracle.xsobel_rtl(R)
+    k = 3
+    xr2 = np.zeros_like(xr); xr2[:, k:] = xr[:, :-k]
+    d1 = run_xsbl(fe640, 0, xl, xr, **dict(RTL, block_size=15))[0]
+    d2 = run_xsbl(fe640, 1, xl, xr2, **dict(RTL, block_size=15))[0]
+    both = (d1 >= (k + 2) * 16) & (d2 >= 32) & (d1 < 60 * 16)
+    assert both.sum() > 50000
+    assert (d1[both] - d2[both] == 16 * k).mean() > 0.98
+
+
+def test_reproject_matches_oracle(u, fe640, oracle):
+    L, R = u.synth_pair(1, 2, 640, 480, 64)
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    fe640.set_bm_params(x_store_offset=1)
+    fe640.submit_rect(0, L, R); b = fe640.wait()
+    d = fe640.receive_disp(b)[0]
+    sx, sy = 640 / 1241, 480 / 376                                   # StereoCameraModel.cpp:108-119 scaling
+    P_l = np.array([[718.856 * sx, 0, 607.1928 * sx, 0], [0, 718.856 * sy, 185.2157 * sy, 0], [0, 0, 1, 0]])
+    P_r = P_l.copy(); P_r[0, 3] = -386.1448 * sx
+    for decim, loc in ((1, False), (4, True), (2, True)):
+        got = fe640.reproject(b, P_l, P_r, decim, loc)[0]
+        want = oracle.reproject(d, P_l, P_r, decim, int(loc))
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) or \
+            ((got == want) | (np.isnan(got) & np.isnan(want))).all()
+
+
+def test_error_behaviour(u):
+    with u.StereoFrontEnd(0, 320, 240, 2) as fe:
+        with pytest.raises(u.U96Error) as e:
+            fe.wait()
+        assert e.value.code == -4                                   # nothing submitted
+        with pytest.raises(u.U96Error):
+            fe.set_bm_params(width=320, height=240, block_size=20)   # even block size
+        with pytest.raises(u.U96Error):
+            fe.set_bm_params(width=320, height=240, profile=0, block_size=21, num_disparities=48)   # RTL: multiple of 32
+        with pytest.raises(u.U96Error):
+            fe.set_bm_params(width=640, height=480)                  # larger than the handle
+        fe.set_bm_params(width=320, height=240, profile=0, block_size=9, num_disparities=32)
+        L, R = u.synth_batch(5, 0, 2, 320, 240, 32)
+        with pytest.raises(u.U96Error) as e:
+            fe.submit_raw(0, L, R)                                   # rect parameters never set
+        assert e.value.code == -4
+        fe.submit_rect(0, L, R)
+        with pytest.raises(u.U96Error) as e:
+            fe.submit_rect(0, L, R)                                  # bank still in flight
+        assert e.value.code == -4
+        assert fe.wait() == 0
+        with pytest.raises(u.U96Error):
+            fe.submit_rect(1, np.concatenate([L, L]), np.concatenate([R, R]))   # batch > max_batch
+        assert fe.kernel_launches() > 0
+
+
+def test_device_resident_submit_is_zero_copy_and_equal(u, oracle):
+    import torch
+    L, R = u.synth_batch(1, 0, 2, 640, 480, 64)
+    with u.StereoFrontEnd(0, 640, 480, 2) as fe:
+        fe.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+        fe.set_bm_params(x_store_offset=1)
+        fe.set_rect_params(u.SHIPPED_RECT_PARAMS)
+        fe.set_stream(torch.cuda.current_stream().cuda_stream)
+        dL, dR = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+        fe.submit_device("raw", 0, dL.data_ptr(), dR.data_ptr(), 640, 2); b = fe.wait()
+        d_dev = fe.receive_disp(b)
+        fe.submit_raw(1, L, R); b = fe.wait()
+        assert np.array_equal(fe.receive_disp(b), d_dev)

@@ -24,6 +24,8 @@
 // Disparity slots: s in [0,D) <-> d = s.  RTL adds the two guard lanes of the first/last dphase
 // (d = -1 -> slot D, d = D -> slot D+1; bm_calc_sad.v:353-418 lanes 0 and 33) which only feed the
 // sub-pixel stage.  OPENCV adds the texture lane (|L - cap| -> slot D).  Slots are padded to DP = D+8.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace u96 {
@@ -407,6 +409,8 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
     const int16_t inv = (c.profile == U96_PROFILE_RTL) ? (int16_t)-1 : (int16_t)-16;
     const size_t total = disp.frame * (size_t)n;
     k_fill16<<<(unsigned)min((size_t)148 * 8, (total + 1023) / 1024), 1024, 0, s>>>(disp.p, total, inv);
+    if (bm_fast_supported(c) && !getenv("U96_BM_GENERIC"))
+        return 1 + launch_bm_fast(xl, xr, pitch, frame, disp, c, n, s);
     BmArgs a;
     if (!bm_fill_args(c, a)) return 1;
     a.xl = xl; a.xr = xr; a.disp = disp.p; a.pitch = pitch; a.frame = frame;

@@ -39,6 +39,10 @@ int  bm_smem_bytes(const BmConfig &c);
 int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
               const BmConfig &c, int n, cudaStream_t s);
 
+bool bm_fast_supported(const BmConfig &c);
+int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
+                   const BmConfig &c, int n, cudaStream_t s);
+
 int launch_reproject(const int16_t *disp, int dpitch, size_t dframe, int W, int H, int n,
                      const double *P_l, const double *P_r, int decim, int flags, float *xyz, cudaStream_t s);
 
