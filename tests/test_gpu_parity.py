@@ -47,7 +47,8 @@ def test_c1_xsobel_matches_reference_golden(u, fe640, golden):
 
 @pytest.mark.parametrize("wsz,uni,thr,mode,crc", [
     (21, 0, 0, 0, 0x3C312D26), (21, 1, 921, 0, 0xF3284A7C), (15, 0, 0, 0, 0xD0650EA3),
-    (9, 1, 800, 1, None), (5, 0, 0, 0, None), (17, 0, 0, 0, None), (31, 0, 0, 0, None), (3, 0, 0, 0, None)])
+    (9, 1, 800, 1, None), (5, 0, 0, 0, None), (17, 0, 0, 0, None), (31, 0, 0, 0, None), (3, 0, 0, 0, None),
+    (19, 0, 0, 0, None), (27, 1, 600, 0, None), (7, 0, 0, 0, None)])
 def test_c1_bm_rtl_bundled_pair(u, fe640, golden, oracle, wsz, uni, thr, mode, crc):
     d = run_xsbl(fe640, 1, golden["xsbl_l"], golden["xsbl_r"], **dict(RTL, block_size=wsz, uni_enable=uni, uni_thr=thr, uni_mode=mode))[0]
     want = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=wsz, ndisp=64, uni_enb=uni, uni_thr=thr, uni_mode=mode)

@@ -43,6 +43,7 @@ struct FastArgs {
     int pitch; size_t frame;
     int dpitch; size_t dframe;
     int W, H, wsz, h, TX, LS, ntx_tiles;
+    int nblk, fix_lo, fix_hi, fix_add;     // window = nblk whole blocks +/- columns [fix_lo, fix_hi)
     int band_h, nbands;
     int ctr_lo, ctr_hi, y_lo, y_hi;
     int x_store_offset, uni_enable, uni_mode, uni_thr, rtl_extended;
@@ -54,6 +55,7 @@ struct FastSmem {
     uint32_t key[F_NC][F_NGR];             //  4096 B   group minima
     uint8_t rcp[2][2][8][F_CS];            //  8704 B   [buffer][newest/oldest][byte shift][..] R row copies
     uint8_t lrow[2][2][F_NC];              //   512 B
+    uint16_t blk[F_NSEG + 4][F_DPS];       //  2880 B   per-segment block sums of the column sums (H warps)
 };
 
 __device__ __forceinline__ uint32_t fprmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
@@ -86,7 +88,7 @@ __device__ __forceinline__ void col_update(uint4 &c, uint32_t ln4, uint32_t lo4,
 // slot position of disparity d inside a column / pixel record
 __device__ __forceinline__ int slot_of(int d) { return (d & ~7) | (7 - (d & 7)); }
 
-template <bool SAT>
+template <bool SAT, int LS>
 __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
 {
     extern __shared__ __align__(16) unsigned char fsm_raw[];
@@ -219,7 +221,6 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
         const int hw = warp - 4;
         const int g = lane & 7;
         const int seg = hw * 4 + (lane >> 3);
-        const int LS = a.LS;
         const int p0 = seg * LS;
         // tie-break constants: slot k of group g <-> d = 8g + 7 - k; lower d wins (bm_calc_det.v strict <)
         uint32_t t[8];
@@ -236,36 +237,58 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
             if (r >= wsz - 1) {
                 const int cb = r & 1;
                 const uint16_t *cg0 = &sm.col[cb][0][8 * g];
-                // ---- window sum of the first pixel of the segment: columns [p0, p0+2h] ----
+                // ---- block sums: every lane adds up the LS columns of its own segment (they are the "oldest"
+                //      operands of its sweep anyway and stay in registers); warp 3 also covers blocks 16..19 ----
+                uint4 ov[LS];
                 uint4 s = make_uint4(0, 0, 0, 0);
-                for (int k = 0; k <= 2 * h; k++) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p0 + k) * F_DPS);
+#pragma unroll
+                for (int j = 0; j < LS; j++) {
+                    ov[j] = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p0 + j) * F_DPS);
+                    s.x += ov[j].x; s.y += ov[j].y; s.z += ov[j].z; s.w += ov[j].w;
+                }
+                *reinterpret_cast<uint4 *>(&sm.blk[seg][8 * g]) = s;
+                if (hw == 3) {
+                    const int eb = F_NSEG + (lane >> 3);
+                    uint4 e = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int j = 0; j < LS; j++) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(eb * LS + j) * F_DPS);
+                        e.x += v.x; e.y += v.y; e.z += v.z; e.w += v.w;
+                    }
+                    *reinterpret_cast<uint4 *>(&sm.blk[eb][8 * g]) = e;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");        // H warps only
+                // ---- window sum of the first pixel = whole blocks +/- a few single columns ----
+                for (int k = 1; k < a.nblk; k++) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(&sm.blk[seg + k][8 * g]);
                     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
                 }
-                uint4 vn = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p0 + 2 * h + 1) * F_DPS);
-                uint4 vo = *reinterpret_cast<const uint4 *>(cg0 + (size_t)p0 * F_DPS);
+                for (int k = a.fix_lo; k < a.fix_hi; k++) {           // single columns added (fix_sign=+1) or removed
+                    const uint4 v = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p0 + k) * F_DPS);
+                    if (a.fix_add) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+                    else           { s.x -= v.x; s.y -= v.y; s.z -= v.z; s.w -= v.w; }
+                }
+                // sliding sweep, fully unrolled (LS is 7 or 8): the newest operand of step j+1 is fetched before
+                // the key arithmetic of step j; the fetch past the last step stays inside the shared struct.
+                const uint16_t *pn = cg0 + (size_t)(p0 + 2 * h + 1) * F_DPS;
+                uint4 vn = *reinterpret_cast<const uint4 *>(pn);
+                uint16_t *sp = &sm.sad[p0][8 * g];
+                uint32_t *kp = &sm.key[p0][g];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (j < LS) {
-                        const int p = p0 + j;
-                        const uint4 sc = s;
-                        // next step's operands first, so the loads overlap the key arithmetic
-                        s.x += vn.x - vo.x; s.y += vn.y - vo.y; s.z += vn.z - vo.z; s.w += vn.w - vo.w;
-                        if (j + 1 < LS) {
-                            vn = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p + 2 * h + 2) * F_DPS);
-                            vo = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p + 1) * F_DPS);
-                        }
-                        const uint32_t k0 = (sc.x << 16) | t[0], k1 = (sc.x & 0xFFFF0000u) | t[1];
-                        const uint32_t k2 = (sc.y << 16) | t[2], k3 = (sc.y & 0xFFFF0000u) | t[3];
-                        const uint32_t k4 = (sc.z << 16) | t[4], k5 = (sc.z & 0xFFFF0000u) | t[5];
-                        const uint32_t k6 = (sc.w << 16) | t[6], k7 = (sc.w & 0xFFFF0000u) | t[7];
-                        uint32_t m = __vimin3_u32(k0, k1, k2);
-                        m = __vimin3_u32(m, k3, k4);
-                        m = __vimin3_u32(m, k5, k6);
-                        m = min(m, k7);
-                        *reinterpret_cast<uint4 *>(&sm.sad[p][8 * g]) = sc;
-                        sm.key[p][g] = m;
-                    }
+                for (int j = 0; j < LS; j++) {
+                    const uint4 sc = s;
+                    s.x += vn.x - ov[j].x; s.y += vn.y - ov[j].y; s.z += vn.z - ov[j].z; s.w += vn.w - ov[j].w;
+                    if (j + 1 < LS) vn = *reinterpret_cast<const uint4 *>(pn + (j + 1) * F_DPS);
+                    const uint32_t k0 = (sc.x << 16) | t[0], k1 = (sc.x & 0xFFFF0000u) | t[1];
+                    const uint32_t k2 = (sc.y << 16) | t[2], k3 = (sc.y & 0xFFFF0000u) | t[3];
+                    const uint32_t k4 = (sc.z << 16) | t[4], k5 = (sc.z & 0xFFFF0000u) | t[5];
+                    const uint32_t k6 = (sc.w << 16) | t[6], k7 = (sc.w & 0xFFFF0000u) | t[7];
+                    uint32_t m = __vimin3_u32(k0, k1, k2);
+                    m = __vimin3_u32(m, k3, k4);
+                    m = __vimin3_u32(m, k5, k6);
+                    m = min(m, k7);
+                    *reinterpret_cast<uint4 *>(sp + j * F_DPS) = sc;
+                    kp[j * F_NGR] = m;
                 }
                 __syncwarp();
                 // ---- per-pixel decision for this warp's own pixels ----
@@ -277,7 +300,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                         const uint32_t w0 = min(ka.x, ka.y), l0 = max(ka.x, ka.y);
                         const uint32_t w1 = min(ka.z, ka.w), l1 = max(ka.z, ka.w);
                         const uint32_t win = min(w0, w1), fin = max(w0, w1);
-                        const uint32_t c1 = ((l1 >> 16) < (l0 >> 16)) ? l1 : l0;
+                        const uint32_t c1 = min(l0, l1);            // value tie -> l0 (lower d)
                         const int d1 = win & 0xFFFF, dfin = fin & 0xFFFF, dc1 = c1 & 0xFFFF;
                         const bool adj0 = (dfin == d1 + 1) || (d1 == dfin + 1);
                         const bool adj1 = (dc1 == d1 + 1) || (d1 == dc1 + 1);
@@ -288,7 +311,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                         const uint32_t w0 = min(kb.x, kb.y), l0 = max(kb.x, kb.y);
                         const uint32_t w1 = min(kb.z, kb.w), l1 = max(kb.z, kb.w);
                         const uint32_t win = min(w0, w1), fin = max(w0, w1);
-                        const uint32_t c1 = ((l1 >> 16) < (l0 >> 16)) ? l1 : l0;
+                        const uint32_t c1 = min(l0, l1);            // value tie -> l0 (lower d)
                         const int d1 = win & 0xFFFF, dfin = fin & 0xFFFF, dc1 = c1 & 0xFFFF;
                         const bool adj0 = (dfin == d1 + 1) || (d1 == dfin + 1);
                         const bool adj1 = (dc1 == d1 + 1) || (d1 == dc1 + 1);
@@ -364,6 +387,12 @@ int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame
     a.W = c.W; a.H = c.H; a.wsz = c.wsz; a.h = c.wsz >> 1;
     a.TX = F_NC - 2 * a.h;
     a.LS = (a.TX + F_NSEG - 1) / F_NSEG;
+    {   // window [0, 2h] of the first pixel of a segment in units of LS-column blocks
+        const int wlen = 2 * a.h + 1, mfull = wlen / a.LS, rem = wlen % a.LS;
+        if (rem <= a.LS - rem) { a.nblk = mfull; a.fix_lo = mfull * a.LS; a.fix_hi = wlen; a.fix_add = 1; }
+        else                   { a.nblk = mfull + 1; a.fix_lo = wlen; a.fix_hi = (mfull + 1) * a.LS; a.fix_add = 0; }
+        if (a.nblk == 0) { a.nblk = 1; a.fix_lo = wlen; a.fix_hi = a.LS; a.fix_add = 0; }      // window shorter than a block
+    }
     a.ctr_lo = c.D + a.h; a.ctr_hi = c.W - 2 - a.h;                    // bm.v:246-252
     a.y_lo = a.h; a.y_hi = c.H - 1 - a.h;
     if (a.ctr_hi < a.ctr_lo || a.y_hi < a.y_lo) return 0;
@@ -376,13 +405,12 @@ int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame
     a.uni_thr = c.uni_thr & 0x3FF; a.rtl_extended = c.rtl_extended;
     const int smem = (int)sizeof(FastSmem);
     dim3 grid(a.ntx_tiles, a.nbands, n);
-    if (sat) {
-        cudaFuncSetAttribute(k_bm_rtl64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_bm_rtl64<true><<<grid, F_THREADS, smem, s>>>(a);
-    } else {
-        cudaFuncSetAttribute(k_bm_rtl64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_bm_rtl64<false><<<grid, F_THREADS, smem, s>>>(a);
-    }
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        kern<<<grid, F_THREADS, smem, s>>>(a);
+    };
+    if (a.LS == 7) { if (sat) go(k_bm_rtl64<true, 7>); else go(k_bm_rtl64<false, 7>); }
+    else           { if (sat) go(k_bm_rtl64<true, 8>); else go(k_bm_rtl64<false, 8>); }
     return 1;
 }
 
