@@ -55,6 +55,7 @@ struct FastSmem {
     uint32_t key[F_NC][F_NGR];             //  4096 B   group minima
     uint8_t rcp[2][2][8][F_CS];            //  8704 B   [buffer][newest/oldest][byte shift][..] R row copies
     uint8_t lrow[2][2][F_NC];              //   512 B
+    uint4 rec[2][F_NC];                    //  4096 B   per-pixel winner records (H -> V), double buffered
     uint16_t blk[F_NSEG + 4][F_DPS];       //  2880 B   per-segment block sums of the column sums (H warps)
 };
 
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
 #pragma unroll
         for (int g = 0; g < F_NGR; g++) c[g] = make_uint4(0, 0, 0, 0);
         uint32_t cg = 0;                                              // guard lanes (d=-1 | d=D<<16)
+        const bool v_active = (warp * 32 < ntx + 2 * h);              // partial last tile: idle warps only keep the barriers
 
         // ---- row staging: thread t<52 stages one 64-bit word of an R row, 64<=t<128 one word of an L row ----
         const bool st_r = (tid < 2 * F_RWORDS), st_l = (tid >= 64);
@@ -181,9 +183,9 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
         stage_store(0);
         __syncthreads();                                              // (A) rows of iteration 0 are staged
 
-        for (int it = 0; it <= nsteps; it++) {
+        for (int it = 0; it <= nsteps + 1; it++) {
             stage_load(it + 1);                                       // global loads in flight during the math
-            if (it < nsteps) {
+            if (it < nsteps && v_active) {
                 const int b = it & 1;
                 const uint32_t ln4 = (uint32_t)sm.lrow[b][0][cx] * 0x01010101u;
                 const uint32_t lo4 = (uint32_t)sm.lrow[b][1][cx] * 0x01010101u;
@@ -211,6 +213,39 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                     *reinterpret_cast<uint32_t *>(colp + F_D) = cg;
                 }
             }
+            // ---- finish the pixels of row it-2 from the H warps' records: sub-pixel, uniqueness, s11.4 output ----
+            {
+                const int r2 = it - 2;
+                if (r2 >= wsz - 1 && cx < ntx) {
+                    const uint4 rc = sm.rec[r2 & 1][cx];
+                    const int L = (int)(rc.x & 0xFFFFu), R = (int)(rc.x >> 16);
+                    const int C = (int)(rc.y & 0xFFFFu);
+                    const uint32_t s_min1 = rc.y & 0xFFFFu, s_min2 = rc.y >> 16;
+                    const int d1 = (int)rc.z;
+                    int q;                                             // bm_calc_frac.v:63-173, floor(128*num/den)
+                    {
+                        const bool cmp = L < R;
+                        const bool neg = (L < C) || (R < C);
+                        const int num = neg ? 0 : (L - R);
+                        const int den = 2 * (cmp ? (R - C) : (L - C));
+                        if (den == 0) q = cmp ? 64 : -64;
+                        else q = (int)floorf(__fdiv_rn((float)(num * 128), (float)den));   // exact: |q|<=64, den<2^17
+                    }
+                    int od = d1, of = q;
+                    if (a.uni_enable) {                                // bm_calc_uni.v:120-134
+                        const uint32_t ratio = (s_min2 == 0) ? 1023u : ((s_min1 * 1024u) / s_min2) & 0x3FFu;
+                        if (ratio > (uint32_t)a.uni_thr) { od = a.uni_mode ? 0xFF : 0; of = a.uni_mode ? -1 : 0; }
+                    }
+                    const int depth = od * 256 + of;                   // bm_obuf2.v:122-154
+                    int out;
+                    if (depth <= 0) out = -1;
+                    else if (a.rtl_extended) out = depth >> 4;
+                    else out = (int)(int16_t)(((depth >> 4) & 0x0FFF) | ((depth & 0x8000) ? 0xF000 : 0));
+                    const int yc = yb0 + (r2 - (wsz - 1));
+                    const int xo = ctr0 + cx + a.x_store_offset;
+                    if (xo < a.W) gout[(size_t)yc * a.dpitch + xo] = (int16_t)out;
+                }
+            }
             stage_store(it + 1);
             asm volatile("bar.sync 1, 256;" ::: "memory");               // (B) one barrier per row
         }
@@ -230,24 +265,28 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
         const int fin_seg = hw * 4 + lane / LS, fin_j = lane % LS;
         const int fp = fin_seg * LS + fin_j;
         const bool fin_ok = (lane < 4 * LS) && (fp < ntx);
+        const bool h_active = (hw * 4 * LS < ntx);                    // partial last tile: this warp has no pixel
+        const int blk_last = (ntx - 1) / LS + a.nblk - 1;             // last block any active segment needs
 
         __syncthreads();                                              // (A)
-        for (int it = 0; it <= nsteps; it++) {
+        for (int it = 0; it <= nsteps + 1; it++) {
             const int r = it - 1;                                     // row index whose column sums are complete
-            if (r >= wsz - 1) {
+            if (r >= wsz - 1 && r < nsteps) {
                 const int cb = r & 1;
                 const uint16_t *cg0 = &sm.col[cb][0][8 * g];
                 // ---- block sums: every lane adds up the LS columns of its own segment (they are the "oldest"
                 //      operands of its sweep anyway and stay in registers); warp 3 also covers blocks 16..19 ----
                 uint4 ov[LS];
                 uint4 s = make_uint4(0, 0, 0, 0);
+                if (hw * 4 <= blk_last) {
 #pragma unroll
-                for (int j = 0; j < LS; j++) {
-                    ov[j] = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p0 + j) * F_DPS);
-                    s.x += ov[j].x; s.y += ov[j].y; s.z += ov[j].z; s.w += ov[j].w;
+                    for (int j = 0; j < LS; j++) {
+                        ov[j] = *reinterpret_cast<const uint4 *>(cg0 + (size_t)(p0 + j) * F_DPS);
+                        s.x += ov[j].x; s.y += ov[j].y; s.z += ov[j].z; s.w += ov[j].w;
+                    }
+                    *reinterpret_cast<uint4 *>(&sm.blk[seg][8 * g]) = s;
                 }
-                *reinterpret_cast<uint4 *>(&sm.blk[seg][8 * g]) = s;
-                if (hw == 3) {
+                if (hw == 3 && F_NSEG <= blk_last) {
                     const int eb = F_NSEG + (lane >> 3);
                     uint4 e = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -258,6 +297,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                     *reinterpret_cast<uint4 *>(&sm.blk[eb][8 * g]) = e;
                 }
                 asm volatile("bar.sync 2, 128;" ::: "memory");        // H warps only
+                if (h_active) {
                 // ---- window sum of the first pixel = whole blocks +/- a few single columns ----
                 for (int k = 1; k < a.nblk; k++) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(&sm.blk[seg + k][8 * g]);
@@ -344,30 +384,10 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                         for (int k = 0; k <= 2 * h; k++) acc += sm.col[cb][fp + k][F_D + 1];
                         R = (int)acc;
                     } else R = sm.sad[fp][slot_of(d1 + 1)];
-                    const int C = (int)s_min1;
-                    int q;                                             // bm_calc_frac.v:63-173, floor(128*num/den)
-                    {
-                        const bool cmp = L < R;
-                        const bool neg = (L < C) || (R < C);
-                        const int num = neg ? 0 : (L - R);
-                        const int den = 2 * (cmp ? (R - C) : (L - C));
-                        if (den == 0) q = cmp ? 64 : -64;
-                        else q = (int)floorf(__fdiv_rn((float)(num * 128), (float)den));   // exact: |q|<=64, den<2^17
-                    }
-                    int od = d1, of = q;
-                    if (a.uni_enable) {                                // bm_calc_uni.v:120-134
-                        const uint32_t ratio = (s_min2 == 0) ? 1023u : ((s_min1 * 1024u) / s_min2) & 0x3FFu;
-                        if (ratio > (uint32_t)a.uni_thr) { od = a.uni_mode ? 0xFF : 0; of = a.uni_mode ? -1 : 0; }
-                    }
-                    const int depth = od * 256 + of;                   // bm_obuf2.v:122-154
-                    int out;
-                    if (depth <= 0) out = -1;
-                    else if (a.rtl_extended) out = depth >> 4;
-                    else out = (int)(int16_t)(((depth >> 4) & 0x0FFF) | ((depth & 0x8000) ? 0xF000 : 0));
-                    const int yc = yb0 + (r - (wsz - 1));
-                    const int xo = ctr0 + fp + a.x_store_offset;
-                    if (xo < a.W) gout[(size_t)yc * a.dpitch + xo] = (int16_t)out;
+                    // winner record for the V warps, which finish the pixel one iteration later
+                    sm.rec[r & 1][fp] = make_uint4((uint32_t)L | ((uint32_t)R << 16), s_min1 | (s_min2 << 16), (uint32_t)d1, 0u);
                 }
+                }   // h_active
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");               // (B)
         }
