@@ -113,6 +113,10 @@ int  u96_receive_rect(u96_handle *h, int bank, uint8_t *L, uint8_t *R);
 int  u96_receive_xsbl(u96_handle *h, int bank, uint8_t *L, uint8_t *R);
 /* Fpga::receiveDepthMap (FPGA.cpp:270-279): CV_16SC1, 16x fixed-point disparity */
 int  u96_receive_disp(u96_handle *h, int bank, int16_t *disp);
+/* asynchronous variant for pipelined callers: enqueues the device->host copy of the disparity behind the bank's
+ * kernels and returns at once; the NEXT u96_wait() that reports this bank also covers the copy.  Must be called
+ * after the submit and before the wait of that bank; `disp` should be pinned (u96_host_alloc). */
+int  u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp);
 /* projectDisparityTo3D over the (decimated) map: Stereo.cpp:157-182, main.cpp:522-551,
  * SensorData.cpp:50-58.  P_l/P_r 3x4 row-major; decim in {1,2,4,8}; xyz = n*(H/decim)*(W/decim)*3 floats.
  * flags bit0: apply StereoCameraModel localTransform (StereoCameraModel.cpp:9-14). */

@@ -68,11 +68,13 @@ __global__ void __launch_bounds__(128) k_rect_remap(const uint8_t *__restrict__ 
                                                     int sp, size_t sf, uint8_t *__restrict__ dL, uint8_t *__restrict__ dR,
                                                     int dp, size_t df, const int2 *__restrict__ map, int W, int H, int n)
 {
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
-    const int lr = blockIdx.z & 1;
-    const int f0 = (blockIdx.z >> 1) * RECT_FPB;
-    if (x4 >= W) return;
+    const int w4 = (W + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;       // flattened (row, 4-pixel group)
+    if (item >= w4 * H) return;
+    const int y = item / w4;
+    const int x4 = (item - y * w4) * 4;
+    const int lr = blockIdx.y & 1;
+    const int f0 = (blockIdx.y >> 1) * RECT_FPB;
     const int2 *m = map + ((size_t)lr * H + y) * W + x4;
     int off[4];          // byte offset of the upper-left tap (may be outside)
     uint32_t w01[4], w23[4];   // packed weights: w00 | w01<<16, w10 | w11<<16   (u1.10 each)
@@ -115,7 +117,7 @@ int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, s
                       Img8 dstL, Img8 dstR, const int2 *map, int W, int H, int n, cudaStream_t s)
 {
     const int tx = 128;
-    dim3 grid((W / 4 + 1 + tx - 1) / tx, H, 2 * ((n + RECT_FPB - 1) / RECT_FPB));
+    dim3 grid((((W + 3) / 4) * H + tx - 1) / tx, 2 * ((n + RECT_FPB - 1) / RECT_FPB));
     k_rect_remap<<<grid, tx, 0, s>>>(srcL, srcR, src_pitch, src_frame, dstL.p, dstR.p, dstL.pitch, dstL.frame, map, W, H, n);
     return 1;
 }

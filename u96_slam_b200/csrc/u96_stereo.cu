@@ -382,6 +382,20 @@ int u96_receive_disp(u96_handle *h, int bank, int16_t *disp)
     return U96_OK;
 }
 
+int u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp)
+{
+    if (!h || bank < 0 || bank > 1 || !disp) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!k.filled || !k.pending) return U96_ERR_STATE;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    const int W = h->bm.width, H = h->bm.height;
+    CK(cudaMemcpy2DAsync(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
+                         cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(k.done, s));                          // wait() now covers the copy as well
+    return U96_OK;
+}
+
 int u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_r[12], int decim, int flags, float *xyz)
 {
     if (!h || bank < 0 || bank > 1 || !P_l || !P_r || !xyz) return U96_ERR_INVALID;

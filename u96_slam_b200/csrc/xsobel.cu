@@ -28,14 +28,16 @@ __device__ __forceinline__ void vsum4(uint32_t a, uint32_t b, uint32_t c, uint32
 }
 
 template <int PROFILE>
-__global__ void __launch_bounds__(128) k_xsobel(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR, int sp, size_t sf,
+__global__ void __launch_bounds__(256) k_xsobel(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR, int sp, size_t sf,
                                                 uint8_t *__restrict__ dL, uint8_t *__restrict__ dR, int dp, size_t df,
                                                 int W, int H, int cap)
 {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    const int y = blockIdx.y;
-    const int lr = blockIdx.z & 1, f = blockIdx.z >> 1;
-    if (x0 >= W) return;
+    const int w16 = (W + 15) >> 4;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;       // flattened (row, 16-pixel group)
+    if (item >= w16 * H) return;
+    const int y = item / w16;
+    const int x0 = (item - y * w16) * 16;
+    const int lr = blockIdx.y & 1, f = blockIdx.y >> 1;
     const uint8_t *src = (lr ? srcR : srcL) + (size_t)f * sf;
     uint8_t *dst = (lr ? dR : dL) + (size_t)f * df + (size_t)y * dp + x0;
 
@@ -106,8 +108,8 @@ __global__ void __launch_bounds__(128) k_xsobel(const uint8_t *__restrict__ srcL
 int launch_xsobel(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
                   Img8 dstL, Img8 dstR, int W, int H, int n, int profile, int cap, cudaStream_t s)
 {
-    const int tx = 128;
-    dim3 grid((align_up(W, 16) / 16 + tx - 1) / tx, H, 2 * n);
+    const int tx = 256;
+    dim3 grid((align_up(W, 16) / 16 * H + tx - 1) / tx, 2 * n);
     if (profile == U96_PROFILE_RTL)
         k_xsobel<U96_PROFILE_RTL><<<grid, tx, 0, s>>>(srcL, srcR, src_pitch, src_frame, dstL.p, dstR.p, dstL.pitch, dstL.frame, W, H, cap);
     else

@@ -1,0 +1,46 @@
+// fpga_test_main.cpp -- the reference's FPGA_TEST loop (slam/src/core/main.cpp:149-187) on the GPU drop-in:
+// capture a pair, setRectImage(bank = iteration % 2), software start, receiveData, dense reprojection of the
+// x4-decimated disparity (main.cpp:522-551).  Prints a checksum per frame; used by tests and INTEGRATION.md.
+//   g++ -std=c++17 -O2 fpga_test_main.cpp -I../../include -L../lib -lu96stereo -Wl,-rpath,../lib -o fpga_test
+#include <cstdio>
+#include <cstdlib>
+
+#include "Fpga.hpp"
+
+static uint64_t splitmix(uint64_t &s) { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                                        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+
+int main(int argc, char **argv)
+{
+    const int frames = argc > 1 ? atoi(argv[1]) : 4;
+    u96::Fpga fpga;
+    if (fpga.registerOpen() != 0 || fpga.memoryOpen() != 0) { fprintf(stderr, "no CUDA device: %s\n", u96_last_cuda_error()); return 2; }
+    const double sx = 640.0 / 1241, sy = 480.0 / 376;                 // StereoCameraModel.cpp:108-119
+    const double P_l[12] = {718.856 * sx, 0, 607.1928 * sx, 0, 0, 718.856 * sy, 185.2157 * sy, 0, 0, 0, 1, 0};
+    double P_r[12]; for (int i = 0; i < 12; i++) P_r[i] = P_l[i]; P_r[3] = -386.1448 * sx;
+    uint64_t seed = 1;
+    for (int it = 0; it < frames; it++) {
+        u96::Mat8 L(480, 640), R(480, 640);
+        for (int y = 0; y < 480; y++)                                   // textured pair with a 12-pixel shift
+            for (int x = 0; x < 640 + 12; x++) {
+                const uint8_t v = (uint8_t)(splitmix(seed) >> 56);
+                if (x >= 12) L.data[(size_t)y * 640 + x - 12] = v;
+                if (x < 640) R.data[(size_t)y * 640 + x] = v;
+            }
+        const int bank = it % 2;                                        // main.cpp:168
+        fpga.setRectImage(bank, L, R);
+        if (fpga.startXsbl(bank) != 0) return 3;
+        u96::Mat8 rl, rr; u96::Mat16 depth;
+        const int active = fpga.receiveData(rl, rr, depth);
+        if (active != bank) return 4;
+        const u96::Mat16 small = u96::decimateDisparity(depth, 4);     // SensorData.cpp:50-58
+        std::vector<float> xyz;
+        if (fpga.projectDisparityTo3D(active, P_l, P_r, 4, true, xyz) != 0) return 5;
+        long long sum = 0, valid = 0, at12 = 0;
+        for (short s : depth.data) { if (s >= 0) { valid++; sum += s; at12 += (s >= 11 * 16 && s <= 13 * 16); } }
+        int pts = 0; for (size_t i = 0; i < xyz.size(); i += 3) pts += (xyz[i] == xyz[i]);
+        printf("frame %d bank %d valid %lld mean_disp %.3f frac_at_12px %.3f decimated %dx%d points %d\n", it, active, valid,
+               valid ? sum / 16.0 / valid : 0.0, valid ? (double)at12 / valid : 0.0, small.cols, small.rows, pts);
+    }
+    return 0;
+}

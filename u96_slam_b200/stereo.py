@@ -90,6 +90,7 @@ def load_library():
     L.u96_receive_rect.argtypes = [vp, i32, u8p, u8p]
     L.u96_receive_xsbl.argtypes = [vp, i32, u8p, u8p]
     L.u96_receive_disp.argtypes = [vp, i32, vp]
+    L.u96_enqueue_receive_disp.argtypes = [vp, i32, vp]
     L.u96_reproject.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), i32, i32, vp]
     L.u96_bank_device_ptr.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_size_t)]
     L.u96_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
@@ -229,6 +230,10 @@ class StereoFrontEnd:
 
     def receive_disp_ptr(self, bank, host_ptr):
         _check(self.L, self.L.u96_receive_disp(self.h, bank, ctypes.c_void_p(host_ptr)), "u96_receive_disp")
+
+    def enqueue_receive_disp_ptr(self, bank, host_ptr):
+        """async D2H of the disparity behind the bank's kernels; the next wait() of this bank covers it"""
+        _check(self.L, self.L.u96_enqueue_receive_disp(self.h, bank, ctypes.c_void_p(host_ptr)), "u96_enqueue_receive_disp")
 
     def reproject(self, bank, P_l, P_r, decim=1, apply_local=False):
         n = self._n[bank]
