@@ -24,8 +24,8 @@ int main(int argc, char **argv)
         for (int y = 0; y < 480; y++)                                   // textured pair with a 12-pixel shift
             for (int x = 0; x < 640 + 12; x++) {
                 const uint8_t v = (uint8_t)(splitmix(seed) >> 56);
-                if (x >= 12) L.data[(size_t)y * 640 + x - 12] = v;
-                if (x < 640) R.data[(size_t)y * 640 + x] = v;
+                if (x < 640) L.data[(size_t)y * 640 + x] = v;          // L(x) = R(x - 12)
+                if (x >= 12) R.data[(size_t)y * 640 + x - 12] = v;
             }
         const int bank = it % 2;                                        // main.cpp:168
         fpga.setRectImage(bank, L, R);
