@@ -271,8 +271,7 @@ def main():
             b = i & 1
             if i >= 2:
                 assert fe2.wait() == b
-            fe2.submit_host_ptr("raw", b, pL.data_ptr(), pR.data_ptr(), W, nb)
-            fe2.enqueue_receive_disp_ptr(b, pD[b].data_ptr())
+            fe2.submit_host_ptr_async("raw", b, pL.data_ptr(), pR.data_ptr(), W, nb, pD[b].data_ptr())
         for _ in range(min(k, 2)):
             fe2.wait()
 
@@ -338,7 +337,7 @@ def main():
                                  f"inputs {in_bytes / 1e6:.0f} MB per step (<L2; intermediates {7 * in_bytes / 2e6:.0f} MB)"},
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(2 * W * H * nb),
                         "d2h_bytes_per_step": int(2 * W * H * nb), "steps": e2e_steps, "checksum": checksum,
-                        "timing": "wall clock around submit/enqueue_receive/wait over two banks, synchronize on both sides"},
+                        "timing": "wall clock around u96_submit_raw_async/u96_wait over two banks, synchronize on both sides"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -98,6 +98,11 @@ int  u96_submit_raw (u96_handle *h, int bank, const uint8_t *L, const uint8_t *R
 int  u96_submit_rect(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n);
 /* sim_dvp.v SimMode 5 (LOAD_XSBL -> bm only): prefiltered pairs */
 int  u96_submit_xsbl(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n);
+/* pipelined variants: the 16x disparity of the batch is also copied to `disp_out` (host, n*H*W int16, ideally
+ * pinned) behind the kernels; batches of >= 64 pairs are cut into chunks whose H2D copy, kernels and D2H copy
+ * overlap on internal streams.  u96_wait() for the bank covers the copies.  disp_out may be NULL. */
+int  u96_submit_raw_async (u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n, int16_t *disp_out);
+int  u96_submit_rect_async(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n, int16_t *disp_out);
 /* same three entry points for inputs already resident in device memory (no copy) */
 int  u96_submit_raw_device (u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n);
 int  u96_submit_rect_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n);

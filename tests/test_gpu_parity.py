@@ -270,3 +270,24 @@ def test_async_receive_pipeline(u, oracle):
         for b in range(2):
             want = oracle.bm_rtl(oracle.xsobel_rtl(L[b]), oracle.xsobel_rtl(R[b]), wsz=21, ndisp=64)
             assert np.array_equal(out[b][0].numpy(), want)
+
+
+def test_pipelined_async_submit_matches(u, oracle):
+    """u96_submit_raw_async: chunked H2D / kernels / D2H pipeline gives the same bits as the plain path."""
+    import torch
+    L, R = u.synth_batch(1, 0, 4, 640, 480, 64)
+    n = 70                                                       # >= 64 -> chunked over the sub-streams
+    hL = torch.from_numpy(np.concatenate([L] * 18)[:n]).pin_memory(); hR = torch.from_numpy(np.concatenate([R] * 18)[:n]).pin_memory()
+    out = torch.empty((n, 480, 640), dtype=torch.int16).pin_memory()
+    with u.StereoFrontEnd(0, 640, 480, n) as fe:
+        fe.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+        fe.set_bm_params(x_store_offset=1)
+        fe.set_rect_params(u.SHIPPED_RECT_PARAMS)
+        fe.submit_host_ptr_async("raw", 0, hL.data_ptr(), hR.data_ptr(), 640, n, out.data_ptr())
+        assert fe.wait() == 0
+        ref = fe.receive_disp(0)
+        assert np.array_equal(out.numpy(), ref)
+        for i in (0, 1, 37, 69):
+            j = i % 4
+            rl, rr = oracle.rectify(L[j], u.SHIPPED_RECT_PARAMS, 0), oracle.rectify(R[j], u.SHIPPED_RECT_PARAMS, 1)
+            assert np.array_equal(out[i].numpy(), oracle.bm_rtl(oracle.xsobel_rtl(rl), oracle.xsobel_rtl(rr), wsz=21, ndisp=64))

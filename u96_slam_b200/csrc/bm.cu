@@ -351,12 +351,26 @@ __global__ void __launch_bounds__(BM_THREADS) k_bm(const BmArgs a)
     }
 }
 
-// fill the whole disparity buffer with the profile's invalid code (borders are never touched by k_bm)
-__global__ void k_fill16(int16_t *p, size_t n, int16_t v)
+// Write the profile's invalid code into the frame border that no CTA of the BM kernels touches:
+// rows [0,y_lo) and (y_hi,H), and in the valid rows the columns left of x_lo / right of x_hi.
+// (bm_obuf2.v skips these bursts and the DISP bank keeps its 0xFF memset, fpga.c:105-106; OpenCV writes -16.)
+constexpr int FB_ROWS = 16;
+__global__ void __launch_bounds__(256) k_fill_border(int16_t *p, int dpitch, size_t dframe, int W, int H,
+                                                     int y_lo, int y_hi, int x_lo, int x_hi, int16_t v)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) p[i] = v;
+    const int y0 = blockIdx.x * FB_ROWS, f = blockIdx.y;
+    const int nright = W - 1 - x_hi, nside = x_lo + nright;        // border pixels of a valid row
+    int16_t *base = p + (size_t)f * dframe;
+    for (int yy = 0; yy < FB_ROWS; yy++) {
+        const int y = y0 + yy;
+        if (y >= H) break;
+        int16_t *row = base + (size_t)y * dpitch;
+        if (y < y_lo || y > y_hi) {
+            for (int x = threadIdx.x; x < W; x += blockDim.x) row[x] = v;
+        } else {
+            for (int i = threadIdx.x; i < nside; i += blockDim.x) row[i < x_lo ? i : x_hi + 1 + (i - x_lo)] = v;
+        }
+    }
 }
 
 static bool bm_fill_args(const BmConfig &c, BmArgs &a)
@@ -407,8 +421,14 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
               const BmConfig &c, int n, cudaStream_t s)
 {
     const int16_t inv = (c.profile == U96_PROFILE_RTL) ? (int16_t)-1 : (int16_t)-16;
-    const size_t total = disp.frame * (size_t)n;
-    k_fill16<<<(unsigned)min((size_t)148 * 8, (total + 1023) / 1024), 1024, 0, s>>>(disp.p, total, inv);
+    {
+        BmArgs b;
+        const bool ok = bm_fill_args(c, b);
+        const int off = (c.profile == U96_PROFILE_RTL) ? c.x_store_offset : 0;
+        // without a valid region the whole frame is border
+        const int y_lo = ok ? b.y_lo : c.H, y_hi = ok ? b.y_hi : c.H, x_lo = ok ? b.ctr_lo + off : c.W, x_hi = ok ? b.ctr_hi + off : c.W;
+        k_fill_border<<<dim3((c.H + FB_ROWS - 1) / FB_ROWS, n), 256, 0, s>>>(disp.p, disp.pitch, disp.frame, c.W, c.H, y_lo, y_hi, x_lo, x_hi, inv);
+    }
     if (bm_fast_supported(c) && !getenv("U96_BM_GENERIC"))
         return 1 + launch_bm_fast(xl, xr, pitch, frame, disp, c, n, s);
     BmArgs a;

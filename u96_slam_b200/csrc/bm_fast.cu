@@ -24,18 +24,16 @@
 // is read in natural memory order (x-d grows as d shrinks).  Guard lanes d=-1 / d=D (sub-pixel only)
 // sit in slots 64/65 and their window sums are formed lazily by the few pixels whose winner is d=0 or
 // d=D-1.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace u96 {
 
-constexpr int F_NC = 128;          // column sums per CTA
 constexpr int F_D = 64;
 constexpr int F_NGR = 8;           // regular 8-disparity groups
 constexpr int F_DPS = 72;          // u16 slots per column in shared memory (64 + 2 guards + pad) -> 144 B rows
-constexpr int F_THREADS = 256;
-constexpr int F_NSEG = 16;         // horizontal segments per tile (4 per H warp)
-constexpr int F_CS = 272;          // bytes per byte-shifted R copy: >= NC + D + 16 and == 16 (mod 128)
-constexpr int F_RWORDS = (F_NC + F_D + 16) / 8;   // 64-bit words staged per R row (26)
+constexpr int F_CS = 272;          // bytes per byte-shifted R copy: >= NC + D + 16 (NC <= 192) and == 16 (mod 128)
 
 struct FastArgs {
     const uint8_t *xl, *xr;
@@ -49,7 +47,9 @@ struct FastArgs {
     int x_store_offset, uni_enable, uni_mode, uni_thr, rtl_extended;
 };
 
+template <int NCW>
 struct FastSmem {
+    static constexpr int F_NC = 32 * NCW, F_NSEG = 4 * NCW;
     uint16_t col[2][F_NC][F_DPS];          // 36864 B   column sums, double buffered (V -> H)
     uint16_t sad[F_NC][F_DPS];             // 18432 B   window sums of the row in flight (H warp private rows)
     uint32_t key[F_NC][F_NGR];             //  4096 B   group minima
@@ -89,11 +89,15 @@ __device__ __forceinline__ void col_update(uint4 &c, uint32_t ln4, uint32_t lo4,
 // slot position of disparity d inside a column / pixel record
 __device__ __forceinline__ int slot_of(int d) { return (d & ~7) | (7 - (d & 7)); }
 
-template <bool SAT, int LS>
-__global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
+// NCW = number of V warps = number of H warps; the tile has 32*NCW column sums and 4*NCW horizontal segments
+template <bool SAT, int LS, int NCW>
+__global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const FastArgs a)
 {
+    constexpr int F_NC = 32 * NCW, F_NSEG = 4 * NCW, F_RWORDS = (F_NC + F_D + 16) / 8, F_LWORDS = F_NC / 4;
+    static_assert(F_NC + F_D + 16 <= F_CS, "R copy stride too small");
+    static_assert(2 * F_RWORDS + 2 * F_LWORDS <= F_NC, "not enough V threads to stage the rows");
     extern __shared__ __align__(16) unsigned char fsm_raw[];
-    FastSmem &sm = *reinterpret_cast<FastSmem *>(fsm_raw);
+    FastSmem<NCW> &sm = *reinterpret_cast<FastSmem<NCW> *>(fsm_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, band = blockIdx.y, f = blockIdx.z;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
     int16_t *gout = a.disp + (size_t)f * a.dframe;
     const int pw = a.pitch >> 2;                  // row pitch in 32-bit words
 
-    if (warp < 4) {
+    if (warp < NCW) {
         // ======================================================================================
         // V role
         // ======================================================================================
@@ -124,10 +128,11 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
         uint32_t cg = 0;                                              // guard lanes (d=-1 | d=D<<16)
         const bool v_active = (warp * 32 < ntx + 2 * h);              // partial last tile: idle warps only keep the barriers
 
-        // ---- row staging: thread t<52 stages one 64-bit word of an R row, 64<=t<128 one word of an L row ----
-        const bool st_r = (tid < 2 * F_RWORDS), st_l = (tid >= 64);
-        const int st_rt = st_r ? (tid / F_RWORDS) : ((tid - 64) >> 5);   // 0 = newest row, 1 = oldest row
-        const int st_q = st_r ? (tid % F_RWORDS) : ((tid - 64) & 31);
+        // ---- row staging: the first 2*RWORDS threads stage one 64-bit word of an R row each, the next 2*LWORDS one word of an L row ----
+        const int lt = tid - 2 * F_RWORDS;
+        const bool st_r = (tid < 2 * F_RWORDS), st_l = (lt >= 0 && lt < 2 * F_LWORDS);
+        const int st_rt = st_r ? (tid / F_RWORDS) : (lt / F_LWORDS);     // 0 = newest row, 1 = oldest row
+        const int st_q = st_r ? (tid % F_RWORDS) : (lt % F_LWORDS);
         uint32_t sw[5];                                               // prefetched aligned words
         auto stage_load = [&](int it) {
             const int y_add = yb0 - h + it;
@@ -247,13 +252,13 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                 }
             }
             stage_store(it + 1);
-            asm volatile("bar.sync 1, 256;" ::: "memory");               // (B) one barrier per row
+            asm volatile("bar.sync 1, %0;" ::"n"(64 * NCW) : "memory");               // (B) one barrier per row
         }
     } else {
         // ======================================================================================
         // H role: horizontal sums + WTA for the row whose column sums were finished last iteration
         // ======================================================================================
-        const int hw = warp - 4;
+        const int hw = warp - NCW;
         const int g = lane & 7;
         const int seg = hw * 4 + (lane >> 3);
         const int p0 = seg * LS;
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                 const int cb = r & 1;
                 const uint16_t *cg0 = &sm.col[cb][0][8 * g];
                 // ---- block sums: every lane adds up the LS columns of its own segment (they are the "oldest"
-                //      operands of its sweep anyway and stay in registers); warp 3 also covers blocks 16..19 ----
+                //      operands of its sweep anyway and stay in registers); the last H warp also covers blocks NSEG..NSEG+3 ----
                 uint4 ov[LS];
                 uint4 s = make_uint4(0, 0, 0, 0);
                 if (hw * 4 <= blk_last) {
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                     }
                     *reinterpret_cast<uint4 *>(&sm.blk[seg][8 * g]) = s;
                 }
-                if (hw == 3 && F_NSEG <= blk_last) {
+                if (hw == NCW - 1 && F_NSEG <= blk_last) {
                     const int eb = F_NSEG + (lane >> 3);
                     uint4 e = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                     }
                     *reinterpret_cast<uint4 *>(&sm.blk[eb][8 * g]) = e;
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");        // H warps only
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * NCW) : "memory");   // H warps only
                 if (h_active) {
                 // ---- window sum of the first pixel = whole blocks +/- a few single columns ----
                 for (int k = 1; k < a.nblk; k++) {
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(F_THREADS, 3) k_bm_rtl64(const FastArgs a)
                 }
                 }   // h_active
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");               // (B)
+            asm volatile("bar.sync 1, %0;" ::"n"(64 * NCW) : "memory");               // (B)
         }
     }
 }
@@ -399,9 +404,11 @@ bool bm_fast_supported(const BmConfig &c)
     return c.profile == U96_PROFILE_RTL && c.D == F_D && c.wsz >= 3 && c.wsz <= 31;
 }
 
-int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
-                   const BmConfig &c, int n, cudaStream_t s)
+template <int NCW>
+static int launch_bm_fast_t(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
+                            const BmConfig &c, int n, cudaStream_t s)
 {
+    constexpr int F_NC = 32 * NCW, F_NSEG = 4 * NCW;
     FastArgs a;
     a.xl = xl; a.xr = xr; a.disp = disp.p; a.pitch = pitch; a.frame = frame; a.dpitch = disp.pitch; a.dframe = disp.frame;
     a.W = c.W; a.H = c.H; a.wsz = c.wsz; a.h = c.wsz >> 1;
@@ -423,15 +430,29 @@ int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame
     else { a.band_h = min(rows, 120); a.nbands = (rows + a.band_h - 1) / a.band_h; }
     a.x_store_offset = c.x_store_offset; a.uni_enable = c.uni_enable; a.uni_mode = c.uni_mode;
     a.uni_thr = c.uni_thr & 0x3FF; a.rtl_extended = c.rtl_extended;
-    const int smem = (int)sizeof(FastSmem);
+    const int smem = (int)sizeof(FastSmem<NCW>);
     dim3 grid(a.ntx_tiles, a.nbands, n);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        kern<<<grid, F_THREADS, smem, s>>>(a);
+        kern<<<grid, 64 * NCW, smem, s>>>(a);
     };
-    if (a.LS == 7) { if (sat) go(k_bm_rtl64<true, 7>); else go(k_bm_rtl64<false, 7>); }
-    else           { if (sat) go(k_bm_rtl64<true, 8>); else go(k_bm_rtl64<false, 8>); }
+    if (a.LS == 7) { if (sat) go(k_bm_rtl64<true, 7, NCW>); else go(k_bm_rtl64<false, 7, NCW>); }
+    else if (a.LS == 8) { if (sat) go(k_bm_rtl64<true, 8, NCW>); else go(k_bm_rtl64<false, 8, NCW>); }
+    else return 0;
     return 1;
+}
+
+// tile width: 4 or 5 warps of columns, whichever wastes fewer column slots on this image width
+int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
+                   const BmConfig &c, int n, cudaStream_t s)
+{
+    const int h = c.wsz >> 1, ncen = c.W - 2 - h - (c.D + h) + 1;
+    auto slots = [&](int ncw) { const int tx = 32 * ncw - 2 * h; return (ncen + tx - 1) / tx * 32 * ncw; };
+    const char *force = getenv("U96_BM_NCW");
+    int ncw = (slots(5) * 100 < slots(4) * 92) ? 5 : 4;              // the wider tile runs at lower occupancy: needs > 8 % less work
+    if (force) ncw = atoi(force);
+    if (ncw == 5) return launch_bm_fast_t<5>(xl, xr, pitch, frame, disp, c, n, s);
+    return launch_bm_fast_t<4>(xl, xr, pitch, frame, disp, c, n, s);
 }
 
 }  // namespace u96

@@ -59,40 +59,117 @@ int launch_rect_build_map(const RectMapParams &rp, int2 *map, cudaStream_t s)
     return 1;
 }
 
-// One thread = 4 consecutive destination pixels of one row of one camera; it keeps the
-// 4 map entries and bilinear weights in registers and loops over FPB frames of the batch,
-// so the map is read once per FPB frames.  Taps outside the source read 0.
+// One thread = 4 consecutive destination pixels of one row of one camera; it keeps the 4 map entries and
+// bilinear weights in registers and loops over FPB frames of the batch, so the map is read once per FPB frames.
+// Taps outside the source read 0.
+//
+// Word path (taken when the source columns of the 4 pixels span <= 6 bytes and their source rows span <= 2 rows,
+// i.e. almost everywhere for a rectifying rotation): the 2 or 3 source rows are fetched as 3 aligned 32-bit
+// words each and funnel-shifted into 8 consecutive bytes; the taps are byte-permuted out and interpolated as
+//   64*s + 2^15 = sum_rows (64*wy_row) * dp4a({left,right},{32-xf,xf}) + 2^15
+// which equals the RTL's sum of four u1.10-weighted taps (rect_intp.v:337-378) by distributivity; the
+// rounding ((s>>9)+1)>>1 == (s+512)>>10 (the 0xFF clamp of rect_intp.v:399-405 is unreachable: s <= 255*1024),
+// so the result is byte 2 of the accumulator and four pixels are packed with three PRMTs.
+// ROWS = 2 when no lane of the warp straddles a source-row step, else 3 (warp-uniform choice, no divergence).
 constexpr int RECT_FPB = 8;
 
-__global__ void __launch_bounds__(128) k_rect_remap(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR,
+template <int ROWS>
+__device__ __forceinline__ void remap_words(const uint32_t *__restrict__ w, uint8_t *__restrict__ dst, int spw, size_t sfw, size_t df,
+                                            int nf, int mis, const uint32_t (&selw)[4], const uint32_t (&wx)[4],
+                                            const uint32_t (&wy)[4][3])
+{
+#pragma unroll 4
+    for (int f = 0; f < nf; f++) {
+        uint32_t lo[ROWS], hi[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const uint32_t a0 = __ldg(w + r * spw), a1 = __ldg(w + r * spw + 1), a2 = __ldg(w + r * spw + 2);
+            lo[r] = __funnelshift_r(a0, a1, mis);
+            hi[r] = __funnelshift_r(a1, a2, mis);
+        }
+        uint32_t acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            acc[k] = 1u << 15;
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) acc[k] += __dp4a(__byte_perm(lo[r], hi[r], selw[k]), wx[k], 0u) * wy[k][r];
+        }
+        const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
+        *reinterpret_cast<uint32_t *>(dst) = __byte_perm(p01, p23, 0x5410);      // pitch is a multiple of 128: always in-row
+        w += sfw;
+        dst += df;
+    }
+}
+
+__global__ void __launch_bounds__(128, 8) k_rect_remap(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR,
                                                     int sp, size_t sf, uint8_t *__restrict__ dL, uint8_t *__restrict__ dR,
                                                     int dp, size_t df, const int2 *__restrict__ map, int W, int H, int n)
 {
     const int w4 = (W + 3) >> 2;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;       // flattened (row, 4-pixel group)
-    if (item >= w4 * H) return;
-    const int y = item / w4;
-    const int x4 = (item - y * w4) * 4;
+    const bool live = item < w4 * H;
+    const int y = live ? item / w4 : 0;
+    const int x4 = live ? (item - y * w4) * 4 : 0;
     const int lr = blockIdx.y & 1;
     const int f0 = (blockIdx.y >> 1) * RECT_FPB;
     const int2 *m = map + ((size_t)lr * H + y) * W + x4;
+    int xi[4], yi[4], xf[4], yf[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int2 e = (live && x4 + k < W) ? m[k] : make_int2(-64, -64);
+        xi[k] = e.x >> 5; xf[k] = e.x & 31; yi[k] = e.y >> 5; yf[k] = e.y & 31;
+    }
+    const uint8_t *src = (lr ? srcR : srcL) + (size_t)f0 * sf;
+    uint8_t *dst = (lr ? dR : dL) + (size_t)f0 * df + (size_t)y * dp + x4;
+    const int nf = live ? min(RECT_FPB, n - f0) : 0;
+
+    int ymin = yi[0], ymax = yi[0];
+#pragma unroll
+    for (int k = 1; k < 4; k++) { ymin = min(ymin, yi[k]); ymax = max(ymax, yi[k]); }
+    bool words = live && (ymin >= 0) && (ymax + 1 < H) && (ymax - ymin <= 1) && (xi[0] >= 0) && (xi[0] + 12 <= sp);
+#pragma unroll
+    for (int k = 1; k < 4; k++) words = words && (xi[k] >= xi[0]) && (xi[k] - xi[0] <= 6);
+#pragma unroll
+    for (int k = 0; k < 4; k++) words = words && (xi[k] + 1 < W);
+    const bool three = words && (ymax != ymin) && (ymin + 2 < H);
+    words = words && (ymax == ymin || three);
+    const unsigned any3 = __any_sync(0xFFFFFFFFu, three);
+
+    if (words) {
+        const int o0 = ymin * sp + xi[0];
+        const int mis = (o0 & 3) * 8;
+        uint32_t selw[4], wx[4], wy[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t dk = (uint32_t)(xi[k] - xi[0]);
+            selw[k] = dk | ((dk + 1) << 4);                           // bytes dk, dk+1 ; the upper two bytes meet zero weights
+            wx[k] = (uint32_t)(32 - xf[k]) | ((uint32_t)xf[k] << 8);  // u8 weights for dp4a
+            const uint32_t a = 64u * (uint32_t)(32 - yf[k]), b = 64u * (uint32_t)yf[k];
+            const bool up = (yi[k] == ymin);
+            wy[k][0] = up ? a : 0u; wy[k][1] = up ? b : a; wy[k][2] = up ? 0u : b;
+        }
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (o0 >> 2);
+        // the third row is only touched when some lane of the warp needs it; lanes at the bottom edge clamp it
+        if (any3) {
+            if (ymin + 2 < H) remap_words<3>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wx, wy);
+            else              remap_words<2>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wx, wy);
+        } else remap_words<2>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wx, wy);
+        return;
+    }
+
+    // generic path (image borders, exotic maps): four independent byte gathers per pixel
     int off[4];          // byte offset of the upper-left tap (may be outside)
     uint32_t w01[4], w23[4];   // packed weights: w00 | w01<<16, w10 | w11<<16   (u1.10 each)
     uint32_t ok[4];      // validity bits of the four taps
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        int2 e = (x4 + k < W) ? m[k] : make_int2(-64, -64);
-        const int xi = e.x >> 5, xf = e.x & 31, yi = e.y >> 5, yf = e.y & 31;
-        w01[k] = (uint32_t)((32 - xf) * (32 - yf)) | ((uint32_t)(xf * (32 - yf)) << 16);
-        w23[k] = (uint32_t)((32 - xf) * yf) | ((uint32_t)(xf * yf) << 16);
-        const bool x0 = (xi >= 0 && xi < W), x1 = (xi + 1 >= 0 && xi + 1 < W);
-        const bool y0 = (yi >= 0 && yi < H), y1 = (yi + 1 >= 0 && yi + 1 < H);
+        w01[k] = (uint32_t)((32 - xf[k]) * (32 - yf[k])) | ((uint32_t)(xf[k] * (32 - yf[k])) << 16);
+        w23[k] = (uint32_t)((32 - xf[k]) * yf[k]) | ((uint32_t)(xf[k] * yf[k]) << 16);
+        const bool x0 = (xi[k] >= 0 && xi[k] < W), x1 = (xi[k] + 1 >= 0 && xi[k] + 1 < W);
+        const bool y0 = (yi[k] >= 0 && yi[k] < H), y1 = (yi[k] + 1 >= 0 && yi[k] + 1 < H);
         ok[k] = (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 2u : 0u) | (x0 && y1 ? 4u : 0u) | (x1 && y1 ? 8u : 0u);
-        off[k] = yi * sp + xi;
+        off[k] = yi[k] * sp + xi[k];
     }
-    const uint8_t *src = (lr ? srcR : srcL) + (size_t)f0 * sf;
-    uint8_t *dst = (lr ? dR : dL) + (size_t)f0 * df + (size_t)y * dp + x4;
-    const int nf = min(RECT_FPB, n - f0);
     for (int f = 0; f < nf; f++) {
         uint32_t out = 0;
 #pragma unroll
@@ -104,10 +181,9 @@ __global__ void __launch_bounds__(128) k_rect_remap(const uint8_t *__restrict__ 
             const uint32_t dr = (ok[k] & 8u) ? __ldg(t + sp + 1) : 0u;
             // u8 * u1.10 summed -> u8.10 ; ((s>>9)+1)>>1 with clamp      rect_intp.v:347-405
             const uint32_t s = ul * (w01[k] & 0xFFFFu) + ur * (w01[k] >> 16) + dl * (w23[k] & 0xFFFFu) + dr * (w23[k] >> 16);
-            const uint32_t r = min(255u, ((s >> 9) + 1u) >> 1);
-            out |= r << (8 * k);
+            out |= min(255u, ((s >> 9) + 1u) >> 1) << (8 * k);
         }
-        *reinterpret_cast<uint32_t *>(dst) = out;      // pitch is a multiple of 128: always in-row
+        *reinterpret_cast<uint32_t *>(dst) = out;
         src += sf;
         dst += df;
     }

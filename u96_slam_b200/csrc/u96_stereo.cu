@@ -4,6 +4,7 @@
 // slam/src/core/FPGA.cpp): it owns two banks (A/B) of every buffer the FPGA keeps in DDR
 // (RECT, XSBL, DISP; StereoBM/src/fpga.h:50-68), fills a bank asynchronously on submit and copies
 // results out on receive.  There is no CPU code path: every stage is a CUDA kernel.
+#include <algorithm>
 #include <deque>
 #include <new>
 #include <string>
@@ -37,6 +38,8 @@ struct Bank {
     int n = 0, from = -1;
     bool filled = false, pending = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t sub[3] = {nullptr, nullptr, nullptr};      // chunk pipeline: H2D / kernels / D2H of different chunks overlap
+    cudaEvent_t sub_ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t done = nullptr, ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -140,6 +143,9 @@ int u96_create(u96_handle **out, int device, int max_w, int max_h, int max_batch
         if (cudaMalloc(&k.disp, img * sizeof(int16_t)) != cudaSuccess) return fail(U96_ERR_NOMEM);
         if (cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking) != cudaSuccess) return fail(U96_ERR_CUDA);
         if (cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming) != cudaSuccess) return fail(U96_ERR_CUDA);
+        for (int i = 0; i < 3; i++)
+            if (cudaStreamCreateWithFlags(&k.sub[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&k.sub_ev[i], cudaEventDisableTiming) != cudaSuccess) return fail(U96_ERR_CUDA);
         for (int i = 0; i < 5; i++)
             if (cudaEventCreate(&k.ev[i]) != cudaSuccess) return fail(U96_ERR_CUDA);
     }
@@ -164,6 +170,7 @@ void u96_destroy(u96_handle *h)
         cudaFree(k.disp);
         if (k.done) cudaEventDestroy(k.done);
         for (int i = 0; i < 5; i++) if (k.ev[i]) cudaEventDestroy(k.ev[i]);
+        for (int i = 0; i < 3; i++) { if (k.sub_ev[i]) cudaEventDestroy(k.sub_ev[i]); if (k.sub[i]) { cudaStreamSynchronize(k.sub[i]); cudaStreamDestroy(k.sub[i]); } }
         if (k.stream) cudaStreamDestroy(k.stream);
     }
     cudaFree(h->map);
@@ -249,8 +256,33 @@ static int ensure_map(u96_handle *h, cudaStream_t s)
     return U96_OK;
 }
 
-// device_src: pointers are device memory; try zero-copy
-static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, const uint8_t *R, int stride, int n, bool device_src)
+// kernels of frames [f0, f0+nf) of a bank on stream s; `prof` records the Perf-style stage events
+static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStream_t s, bool prof)
+{
+    const int W = h->bm.width, H = h->bm.height, pitch = h->pitch;
+    const size_t frame = (size_t)pitch * H, o = (size_t)f0 * frame;
+    const Img8 rectL{k.rect[0] + o, pitch, frame}, rectR{k.rect[1] + o, pitch, frame};
+    const Img8 xsblL{k.xsbl[0] + o, pitch, frame}, xsblR{k.xsbl[1] + o, pitch, frame};
+    const Img16 disp{k.disp + o, pitch, frame};
+    if (from == FROM_RAW)
+        h->launches += launch_rect_remap(k.cur_raw[0] + (size_t)f0 * k.raw_frame, k.cur_raw[1] + (size_t)f0 * k.raw_frame, k.raw_pitch,
+                                         k.raw_frame, rectL, rectR, h->map, W, H, nf, s);
+    if (prof) CK(cudaEventRecord(k.ev[2], s));
+    if (from <= FROM_RECT)
+        h->launches += launch_xsobel(k.cur_rect[0] + (size_t)f0 * k.rect_frame, k.cur_rect[1] + (size_t)f0 * k.rect_frame, k.rect_pitch,
+                                     k.rect_frame, xsblL, xsblR, W, H, nf, h->bm.profile, h->bm.prefilter_cap, s);
+    if (prof) CK(cudaEventRecord(k.ev[3], s));
+    h->launches += launch_bm(k.cur_xsbl[0] + (size_t)f0 * k.xsbl_frame, k.cur_xsbl[1] + (size_t)f0 * k.xsbl_frame, k.xsbl_pitch,
+                             k.xsbl_frame, disp, bm_config(h->bm), nf, s);
+    if (prof) CK(cudaEventRecord(k.ev[4], s));
+    return U96_OK;
+}
+
+// device_src: pointers are device memory (zero-copy when aligned).  disp_out (host, optional): the disparity is
+// copied out behind the kernels; large host batches are cut into chunks that flow through three sub-streams so
+// the H2D copy, the kernels and the D2H copy of different chunks overlap (both copy engines + SMs busy).
+static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, const uint8_t *R, int stride, int n, bool device_src,
+                         int16_t *disp_out = nullptr)
 {
     if (!h || !L || !R || bank < 0 || bank > 1 || n <= 0 || n > h->maxB) return U96_ERR_INVALID;
     const int W = h->bm.width, H = h->bm.height;
@@ -267,41 +299,53 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     uint8_t *dstbuf[2];
     for (int i = 0; i < 2; i++) dstbuf[i] = (from == FROM_RAW) ? k.raw[i] : (from == FROM_RECT) ? k.rect[i] : k.xsbl[i];
     const uint8_t *src[2] = {L, R};
-    const uint8_t *cur[2];
-    int cur_pitch; size_t cur_frame;
     const bool zero_copy = device_src && (stride % 16 == 0) && (stride >= align_up(W, 16)) &&
                            (((uintptr_t)L | (uintptr_t)R) % 16 == 0);
-    if (zero_copy) {
-        cur[0] = L; cur[1] = R; cur_pitch = stride; cur_frame = (size_t)stride * H;
-    } else {
-        for (int i = 0; i < 2; i++)
-            CK(cudaMemcpy2DAsync(dstbuf[i], pitch, src[i], stride, W, (size_t)H * n,
-                                 device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-        cur[0] = dstbuf[0]; cur[1] = dstbuf[1]; cur_pitch = pitch; cur_frame = frame;
-    }
-    if (h->profiling) CK(cudaEventRecord(k.ev[1], s));
-
-    const Img8 rectL{k.rect[0], pitch, frame}, rectR{k.rect[1], pitch, frame};
-    const Img8 xsblL{k.xsbl[0], pitch, frame}, xsblR{k.xsbl[1], pitch, frame};
-    const Img16 disp{k.disp, pitch, frame};
+    const uint8_t *cur[2] = {zero_copy ? L : dstbuf[0], zero_copy ? R : dstbuf[1]};
+    const int cur_pitch = zero_copy ? stride : pitch;
+    const size_t cur_frame = zero_copy ? (size_t)stride * H : frame;
     if (from == FROM_RAW) {
         k.cur_raw[0] = cur[0]; k.cur_raw[1] = cur[1]; k.raw_pitch = cur_pitch; k.raw_frame = cur_frame;
-        h->launches += launch_rect_remap(cur[0], cur[1], cur_pitch, cur_frame, rectL, rectR, h->map, W, H, n, s);
         k.cur_rect[0] = k.rect[0]; k.cur_rect[1] = k.rect[1]; k.rect_pitch = pitch; k.rect_frame = frame;
     } else if (from == FROM_RECT) {
         k.cur_rect[0] = cur[0]; k.cur_rect[1] = cur[1]; k.rect_pitch = cur_pitch; k.rect_frame = cur_frame;
     }
-    if (h->profiling) CK(cudaEventRecord(k.ev[2], s));
-    if (from <= FROM_RECT) {
-        h->launches += launch_xsobel(k.cur_rect[0], k.cur_rect[1], k.rect_pitch, k.rect_frame, xsblL, xsblR, W, H, n,
-                                     h->bm.profile, h->bm.prefilter_cap, s);
-        k.cur_xsbl[0] = k.xsbl[0]; k.cur_xsbl[1] = k.xsbl[1]; k.xsbl_pitch = pitch; k.xsbl_frame = frame;
+    if (from <= FROM_RECT) { k.cur_xsbl[0] = k.xsbl[0]; k.cur_xsbl[1] = k.xsbl[1]; k.xsbl_pitch = pitch; k.xsbl_frame = frame; }
+    else { k.cur_xsbl[0] = cur[0]; k.cur_xsbl[1] = cur[1]; k.xsbl_pitch = cur_pitch; k.xsbl_frame = cur_frame; }
+
+    const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= 64;
+    if (!pipelined) {
+        if (!zero_copy)
+            for (int i = 0; i < 2; i++)
+                CK(cudaMemcpy2DAsync(dstbuf[i], pitch, src[i], stride, W, (size_t)H * n,
+                                     device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        if (h->profiling) CK(cudaEventRecord(k.ev[1], s));
+        const int rc = run_range(h, k, from, 0, n, s, h->profiling);
+        if (rc != U96_OK) return rc;
+        if (disp_out)
+            CK(cudaMemcpy2DAsync(disp_out, (size_t)W * 2, k.disp, (size_t)pitch * 2, (size_t)W * 2, (size_t)H * n, cudaMemcpyDeviceToHost, s));
     } else {
-        k.cur_xsbl[0] = cur[0]; k.cur_xsbl[1] = cur[1]; k.xsbl_pitch = cur_pitch; k.xsbl_frame = cur_frame;
+        const int nchunks = std::min(8, n / 32);
+        const int csz = (n + nchunks - 1) / nchunks;
+        CK(cudaEventRecord(k.done, s));                       // the sub-streams start behind whatever the bank stream holds
+        for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(k.sub[i], k.done, 0));
+        for (int c = 0, f0 = 0; f0 < n; c++, f0 += csz) {
+            const int nf = std::min(csz, n - f0);
+            cudaStream_t cs = k.sub[c % 3];
+            for (int i = 0; i < 2; i++)
+                CK(cudaMemcpy2DAsync(dstbuf[i] + (size_t)f0 * frame, pitch, src[i] + (size_t)f0 * stride * H, stride, W, (size_t)H * nf,
+                                     cudaMemcpyHostToDevice, cs));
+            const int rc = run_range(h, k, from, f0, nf, cs, false);
+            if (rc != U96_OK) return rc;
+            if (disp_out)
+                CK(cudaMemcpy2DAsync(disp_out + (size_t)f0 * W * H, (size_t)W * 2, k.disp + (size_t)f0 * frame, (size_t)pitch * 2,
+                                     (size_t)W * 2, (size_t)H * nf, cudaMemcpyDeviceToHost, cs));
+        }
+        for (int i = 0; i < 3; i++) {                         // join: the bank stream (and `done`) follows all chunks
+            CK(cudaEventRecord(k.sub_ev[i], k.sub[i]));
+            CK(cudaStreamWaitEvent(s, k.sub_ev[i], 0));
+        }
     }
-    if (h->profiling) CK(cudaEventRecord(k.ev[3], s));
-    h->launches += launch_bm(k.cur_xsbl[0], k.cur_xsbl[1], k.xsbl_pitch, k.xsbl_frame, disp, bm_config(h->bm), n, s);
-    if (h->profiling) CK(cudaEventRecord(k.ev[4], s));
     CK(cudaGetLastError());
     CK(cudaEventRecord(k.done, s));
     k.n = n; k.from = from; k.filled = true; k.pending = true;
@@ -334,6 +378,10 @@ int u96_submit_rect(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R,
 { return submit_common(h, bank, FROM_RECT, L, R, stride, n, false); }
 int u96_submit_xsbl(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n)
 { return submit_common(h, bank, FROM_XSBL, L, R, stride, n, false); }
+int u96_submit_raw_async(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n, int16_t *disp_out)
+{ return submit_common(h, bank, FROM_RAW, L, R, stride, n, false, disp_out); }
+int u96_submit_rect_async(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n, int16_t *disp_out)
+{ return submit_common(h, bank, FROM_RECT, L, R, stride, n, false, disp_out); }
 int u96_submit_raw_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n)
 { return submit_common(h, bank, FROM_RAW, (const uint8_t *)dL, (const uint8_t *)dR, stride, n, true); }
 int u96_submit_rect_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n)

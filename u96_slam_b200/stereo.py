@@ -86,6 +86,8 @@ def load_library():
     for name in ("u96_submit_raw", "u96_submit_rect", "u96_submit_xsbl",
                  "u96_submit_raw_device", "u96_submit_rect_device", "u96_submit_xsbl_device"):
         getattr(L, name).argtypes = [vp, i32, u8p, u8p, i32, i32]
+    L.u96_submit_raw_async.argtypes = [vp, i32, u8p, u8p, i32, i32, vp]
+    L.u96_submit_rect_async.argtypes = [vp, i32, u8p, u8p, i32, i32, vp]
     L.u96_wait.argtypes = [vp, ctypes.POINTER(i32)]
     L.u96_receive_rect.argtypes = [vp, i32, u8p, u8p]
     L.u96_receive_xsbl.argtypes = [vp, i32, u8p, u8p]
@@ -203,6 +205,12 @@ class StereoFrontEnd:
     def submit_host_ptr(self, kind, bank, ptr_l, ptr_r, stride, n):
         fn = {"raw": self.L.u96_submit_raw, "rect": self.L.u96_submit_rect, "xsbl": self.L.u96_submit_xsbl}[kind]
         _check(self.L, fn(self.h, bank, ctypes.c_void_p(ptr_l), ctypes.c_void_p(ptr_r), stride, n), fn.__name__)
+        self._n[bank] = n
+
+    def submit_host_ptr_async(self, kind, bank, ptr_l, ptr_r, stride, n, disp_out_ptr):
+        """pipelined submit: H2D, kernels and the D2H of the disparity overlap chunk by chunk"""
+        fn = {"raw": self.L.u96_submit_raw_async, "rect": self.L.u96_submit_rect_async}[kind]
+        _check(self.L, fn(self.h, bank, ctypes.c_void_p(ptr_l), ctypes.c_void_p(ptr_r), stride, n, ctypes.c_void_p(disp_out_ptr)), fn.__name__)
         self._n[bank] = n
 
     def wait(self):
