@@ -52,7 +52,8 @@ struct FastSmem {
     static constexpr int F_NC = 32 * NCW, F_NSEG = 4 * NCW;
     uint16_t col[2][F_NC][F_DPS];          // 36864 B   column sums, double buffered (V -> H)
     uint16_t sad[F_NC][F_DPS];             // 18432 B   window sums of the row in flight (H warp private rows)
-    uint32_t key[F_NC][F_NGR];             //  4096 B   group minima
+    uint32_t key[2][F_NC * 4 + 16];        //  4224 B   group minima: [group half][pixel][4], halves 16 banks apart
+    uint32_t guard[2][F_NC];               //  1024 B   column sums of the guard lanes (d=-1 | d=D << 16), double buffered
     uint8_t rcp[2][2][8][F_CS];            //  8704 B   [buffer][newest/oldest][byte shift][..] R row copies
     uint8_t lrow[2][2][F_NC];              //   512 B
     uint4 rec[2][F_NC];                    //  4096 B   per-pixel winner records (H -> V), double buffered
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const
     const int ctr0 = a.ctr_lo + tile * a.TX;
     const int ntx = min(a.TX, a.ctr_hi - ctr0 + 1);
     const int xs = ctr0 - h;                      // image x of column 0
-    const int xr0 = xs - F_D - 8;                 // image x of staged R byte 0
+    const int xr0 = xs - F_D - 7;                 // image x of staged R byte 0 (makes the byte shift of column cx equal cx & 7)
     const int yb0 = a.y_lo + band * a.band_h;
     const int yb1 = min(a.y_hi + 1, yb0 + a.band_h);
     const int nsteps = (wsz - 1) + (yb1 - yb0);   // rows fed to the column sums
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const
         // V role
         // ======================================================================================
         const int cx = tid;                                           // 0..127
-        const int sh = (cx + 1) & 7;                                  // byte shift of this column's R window
-        const int qb = ((cx + 1 - sh) >> 3) + F_D / 8;                // 64-bit word of group 0
+        const int sh = cx & 7;                                        // byte shift of this column's R window
+        const int qb = (cx >> 3) + F_D / 8;                           // 64-bit word of group 0
         uint4 c[F_NGR];
 #pragma unroll
         for (int g = 0; g < F_NGR; g++) c[g] = make_uint4(0, 0, 0, 0);
@@ -205,8 +206,8 @@ __global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const
                 // guard lanes: d=-1 reads R(x+1), d=D reads R(x-D)          (bm_calc_sad.v lanes 0 and 33)
                 {
                     const uint8_t *r0n = &sm.rcp[b][0][0][0], *r0o = &sm.rcp[b][1][0][0];
-                    const uint32_t gn = r0n[cx + F_D + 9] | ((uint32_t)r0n[cx + 8] << 8);
-                    const uint32_t go = r0o[cx + F_D + 9] | ((uint32_t)r0o[cx + 8] << 8);
+                    const uint32_t gn = r0n[cx + F_D + 8] | ((uint32_t)r0n[cx + 7] << 8);
+                    const uint32_t go = r0o[cx + F_D + 8] | ((uint32_t)r0o[cx + 7] << 8);
                     const uint32_t an = __vabsdiffu4(ln4, fprmt(gn, ln4, 0x5410));
                     const uint32_t ao = __vabsdiffu4(lo4, fprmt(go, lo4, 0x5410));
                     if (SAT) {
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const
                     } else {
                         cg += fprmt(an, 0, 0x4140) - fprmt(ao, 0, 0x4140);
                     }
-                    *reinterpret_cast<uint32_t *>(colp + F_D) = cg;
+                    sm.guard[b][cx] = cg;
                 }
             }
             // ---- finish the pixels of row it-2 from the H warps' records: sub-pixel, uniqueness, s11.4 output ----
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const
                 const uint16_t *pn = cg0 + (size_t)(p0 + 2 * h + 1) * F_DPS;
                 uint4 vn = *reinterpret_cast<const uint4 *>(pn);
                 uint16_t *sp = &sm.sad[p0][8 * g];
-                uint32_t *kp = &sm.key[p0][g];
+                uint32_t *kp = &sm.key[g >> 2][p0 * 4 + (g & 3)];
 #pragma unroll
                 for (int j = 0; j < LS; j++) {
                     const uint4 sc = s;
@@ -333,13 +334,13 @@ __global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const
                     m = __vimin3_u32(m, k5, k6);
                     m = min(m, k7);
                     *reinterpret_cast<uint4 *>(sp + j * F_DPS) = sc;
-                    kp[j * F_NGR] = m;
+                    kp[j * 4] = m;
                 }
                 __syncwarp();
                 // ---- per-pixel decision for this warp's own pixels ----
                 if (fin_ok) {
-                    const uint4 ka = *reinterpret_cast<const uint4 *>(&sm.key[fp][0]);
-                    const uint4 kb = *reinterpret_cast<const uint4 *>(&sm.key[fp][4]);
+                    const uint4 ka = *reinterpret_cast<const uint4 *>(&sm.key[0][fp * 4]);
+                    const uint4 kb = *reinterpret_cast<const uint4 *>(&sm.key[1][fp * 4]);
                     uint32_t s_min1, s_min2, s_d1, s_d2;
                     {   // dphase 0: levels 4-5 of the tournament and the approximate min2 (bm_calc_det.v:268-411)
                         const uint32_t w0 = min(ka.x, ka.y), l0 = max(ka.x, ka.y);
@@ -381,12 +382,12 @@ __global__ void __launch_bounds__(64 * NCW, (NCW <= 4) ? 3 : 2) k_bm_rtl64(const
                     int L, R;
                     if (d1 == 0) {                                     // guard lane d=-1: lazy window sum
                         uint32_t acc = 0;
-                        for (int k = 0; k <= 2 * h; k++) acc += sm.col[cb][fp + k][F_D];
+                        for (int k = 0; k <= 2 * h; k++) acc += sm.guard[cb][fp + k] & 0xFFFFu;
                         L = (int)acc;
                     } else L = sm.sad[fp][slot_of(d1 - 1)];
                     if (d1 == F_D - 1) {                               // guard lane d=D
                         uint32_t acc = 0;
-                        for (int k = 0; k <= 2 * h; k++) acc += sm.col[cb][fp + k][F_D + 1];
+                        for (int k = 0; k <= 2 * h; k++) acc += sm.guard[cb][fp + k] >> 16;
                         R = (int)acc;
                     } else R = sm.sad[fp][slot_of(d1 + 1)];
                     // winner record for the V warps, which finish the pixel one iteration later
