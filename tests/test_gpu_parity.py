@@ -291,3 +291,49 @@ def test_pipelined_async_submit_matches(u, oracle):
             j = i % 4
             rl, rr = oracle.rectify(L[j], u.SHIPPED_RECT_PARAMS, 0), oracle.rectify(R[j], u.SHIPPED_RECT_PARAMS, 1)
             assert np.array_equal(out[i].numpy(), oracle.bm_rtl(oracle.xsobel_rtl(rl), oracle.xsobel_rtl(rr), wsz=21, ndisp=64))
+
+
+def test_c5_slam_loop_octomap(u, oracle, tmp_path):
+    """BASELINE config C5: BM disparity -> x4 decimation -> reprojectTo3D -> pose -> OctoMap (main.cpp:495-561) through
+    host/slam_loop (C++ shim + the reference's vendored OctoMap), point set checked against the oracle."""
+    import os, subprocess, struct
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "u96_slam_b200", "host", "slam_loop")
+    if not os.path.exists(exe):
+        pytest.skip("slam_loop not built (needs the reference's OctoMap sources at build time)")
+    N = 5
+    seq = tmp_path / "seq.bin"
+    frames = [u.synth_pair(1, i, 640, 480, 64, x_drift=1) for i in range(N)]
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i", 640, 480, N))
+        for L, R in frames:
+            f.write(L.tobytes()); f.write(R.tobytes())
+    step = (0.0, -0.05, 0.0)
+    out = subprocess.run([exe, str(seq), str(tmp_path / "slam.bt")] + [str(s) for s in step], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    tok = out.stdout.split()
+    got = {tok[i]: tok[i + 1] for i in range(0, len(tok), 2)}
+    assert os.path.getsize(tmp_path / "slam.bt") > 1000 and int(got["leaf_nodes"]) > 1000
+    # oracle side of the same loop
+    sx, sy = 640.0 / 1241, 480.0 / 376
+    P_l = np.array([[718.856 * sx, 0, 607.1928 * sx, 0], [0, 718.856 * sy, 185.2157 * sy, 0], [0, 0, 1, 0]])
+    P_r = P_l.copy(); P_r[0, 3] = -386.1448 * sx
+    finite = inserted = 0
+    checksum = 0.0
+    for i, (L, R) in enumerate(frames):
+        d = oracle.bm_rtl(oracle.xsobel_rtl(L), oracle.xsobel_rtl(R), wsz=21, ndisp=64)
+        pts = oracle.reproject(d, P_l, P_r, 4, 1).reshape(-1, 3)
+        ok = np.isfinite(pts).all(axis=1)
+        finite += int(ok.sum())
+        p = pts[ok]
+        o = np.array([np.float32(step[k]) * np.float32(i) for k in range(3)], np.float32)
+        w = (p + o).astype(np.float32)
+        v = (w - o).astype(np.float32)
+        rng = np.sqrt((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2]).astype(np.float32).astype(np.float64))
+        keep = rng <= 25.0
+        inserted += int(keep.sum())
+        wk = w[keep].astype(np.float64)
+        checksum += float((wk[:, 0] + 2.0 * wk[:, 1] + 3.0 * wk[:, 2]).sum())
+    assert int(got["finite_points"]) == finite
+    assert abs(int(got["inserted"]) - inserted) <= 2                  # float sqrt at exactly the 25 m gate
+    assert abs(float(got["checksum"]) - checksum) <= 1e-6 * abs(checksum) + 200.0
