@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define U96_ABI_VERSION 1
+#define U96_ABI_VERSION 2
 
 enum {
     U96_OK = 0,
@@ -64,6 +64,10 @@ typedef struct {
     int32_t uni_enable, uni_mode, uni_thr;   /* RTL only: UniFiltCtrl fields          */
     int32_t x_store_offset;     /* RTL only: 1 = DISP bank layout (bm_obuf2.v:125)   */
     int32_t rtl_extended;       /* RTL only: 1 = zero-extend >>4 (needed for D>128)  */
+    /* OPENCV only: the post filters cv::StereoBM::compute applies (main.cpp:210-212) */
+    int32_t disp12_max_diff;    /* validateDisparity threshold in pixels, < 0 = off  */
+    int32_t speckle_window_size;/* filterSpeckles maxSpeckleSize, 0 = off            */
+    int32_t speckle_range;      /* filterSpeckles maxDiff (on the 16x values, as cv::StereoBM passes it) */
 } u96_bm_params;
 
 /* = struct RECT_PARAM (StereoBM/src/fpga.h:250-260) / FPGA_REG_RECT (fpga.h:178-214);

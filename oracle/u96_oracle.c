@@ -365,6 +365,14 @@ int orc_bm_rtl(const uint8_t *xl, const uint8_t *xr, int W, int H,
 int orc_bm_cv(const uint8_t *pl, const uint8_t *pr, int W, int H,
               const orc_bm_cv_params *p, int16_t *disp)
 {
+    return orc_bm_cv_cost(pl, pr, W, H, p, disp, NULL);
+}
+
+/* same, also returning the winning SAD of every VALID pixel (the `cost` image cv::StereoBM hands to
+ * validateDisparity); entries of invalid pixels are left untouched, as in OpenCV. */
+int orc_bm_cv_cost(const uint8_t *pl, const uint8_t *pr, int W, int H,
+                   const orc_bm_cv_params *p, int16_t *disp, int16_t *cost)
+{
     const int wsz = p->wsz, D = p->ndisp, h = wsz >> 1, cap = p->prefilter_cap;
     if (wsz < 5 || !(wsz & 1) || D < 16 || (D & 15)) return -1;
     for (int i = 0; i < W * H; i++) disp[i] = -16;
@@ -411,10 +419,79 @@ int orc_bm_cv(const uint8_t *pl, const uint8_t *pr, int W, int H,
             int32_t den = pp + nn - 2 * minsad + abs(pp - nn);
             int32_t frac = den ? ((pp - nn) * 256) / den : 0;      /* C division: toward zero */
             disp[(size_t)y * W + x] = (int16_t)((mind * 256 + frac + 15) >> 4);
+            if (cost) cost[(size_t)y * W + x] = (int16_t)minsad;
         }
     }
     free(sad); free(colsum); free(coltex);
     return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* cv::StereoBM post filters as enabled at slam/src/core/main.cpp:210-212      */
+/* (OpenCV calib3d: validateDisparity, filterSpeckles; restated from the       */
+/*  published algorithm, pinned against cv2 4.13 in tests)                      */
+/* ------------------------------------------------------------------------ */
+void orc_validate_disparity(int16_t *disp, const int16_t *cost, int W, int H, int min_d, int ndisp, int disp12_max_diff)
+{
+    const int maxD = min_d + ndisp;
+    const int minX1 = maxD > 0 ? maxD : 0, maxX1 = W + (min_d < 0 ? min_d : 0);
+    const int INVALID = (min_d - 1) * 16;
+    const int maxdiff = disp12_max_diff * 16;
+    int *d2 = (int *)malloc(sizeof(int) * 2 * (size_t)W), *c2 = d2 + W;
+    for (int y = 0; y < H; y++) {
+        int16_t *dp = disp + (size_t)y * W;
+        const int16_t *cp = cost + (size_t)y * W;
+        for (int x = 0; x < W; x++) { d2[x] = INVALID; c2[x] = 0x7FFFFFFF; }
+        for (int x = minX1; x < maxX1; x++) {          /* right-image disparity: cheapest match wins, first wins ties */
+            const int d = dp[x], c = cp[x];
+            if (d == INVALID) continue;
+            const int x2 = x - ((d + 8) >> 4);
+            if (c2[x2] > c) { c2[x2] = c; d2[x2] = d; }
+        }
+        for (int x = minX1; x < maxX1; x++) {          /* rounded towards -inf and +inf: invalid only if both disagree */
+            const int d = dp[x];
+            if (d == INVALID) continue;
+            const int d0 = d >> 4, d1 = (d + 15) >> 4, x0 = x - d0, x1 = x - d1;
+            if ((0 <= x0 && x0 < W && d2[x0] > INVALID && abs(d2[x0] - d) > maxdiff) &&
+                (0 <= x1 && x1 < W && d2[x1] > INVALID && abs(d2[x1] - d) > maxdiff))
+                dp[x] = (int16_t)INVALID;
+        }
+    }
+    free(d2);
+}
+
+/* 4-connected regions of pixels != new_val whose neighbours differ by <= max_diff; regions of at most
+ * max_size pixels become new_val.  (Region membership is the transitive closure of the pairwise relation,
+ * so the result does not depend on the traversal order.) */
+void orc_filter_speckles(int16_t *img, int W, int H, int new_val, int max_size, int max_diff)
+{
+    int *label = (int *)calloc((size_t)W * H, sizeof(int));
+    int *stack = (int *)malloc(sizeof(int) * (size_t)W * H);
+    int cur = 0;
+    for (int i0 = 0; i0 < W * H; i0++) {
+        if (img[i0] == new_val || label[i0]) continue;
+        cur++;
+        int sp = 0, count = 0;
+        stack[sp++] = i0; label[i0] = cur;
+        int first = i0; (void)first;
+        /* pass 1: flood fill and count */
+        int *members = stack;                          /* members are recorded in place: visited order */
+        int head = 0;
+        while (head < sp) {
+            const int i = members[head++];
+            count++;
+            const int x = i % W, y = i / W, v = img[i];
+            const int nb[4] = {x > 0 ? i - 1 : -1, x < W - 1 ? i + 1 : -1, y > 0 ? i - W : -1, y < H - 1 ? i + W : -1};
+            for (int k = 0; k < 4; k++) {
+                const int j = nb[k];
+                if (j < 0 || label[j] || img[j] == new_val) continue;
+                if (abs((int)img[j] - v) <= max_diff) { label[j] = cur; members[sp++] = j; }
+            }
+        }
+        if (count <= max_size)
+            for (int k = 0; k < sp; k++) img[members[k]] = (int16_t)new_val;
+    }
+    free(label); free(stack);
 }
 
 /* ------------------------------------------------------------------------ */

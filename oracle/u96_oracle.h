@@ -84,6 +84,12 @@ typedef struct {
 int orc_bm_cv(const uint8_t *pl, const uint8_t *pr, int W, int H,
               const orc_bm_cv_params *p, int16_t *disp);
 
+int orc_bm_cv_cost(const uint8_t *pl, const uint8_t *pr, int W, int H,
+                   const orc_bm_cv_params *p, int16_t *disp, int16_t *cost);
+/* cv::StereoBM post filters (main.cpp:210-212): validateDisparity(disp12MaxDiff) then filterSpeckles */
+void orc_validate_disparity(int16_t *disp, const int16_t *cost, int W, int H, int min_d, int ndisp, int disp12_max_diff);
+void orc_filter_speckles(int16_t *img, int W, int H, int new_val, int max_size, int max_diff);
+
 /* ---- disparity -> 3-D: slam/src/core/Stereo.cpp:157-182, main.cpp:522-551 - */
 /* P_l, P_r: 3x4 row-major projection matrices.  decim = 1 or 4
  * (SensorData.cpp:50-58).  xyz: (W/decim)*(H/decim)*3 floats, NaN if d<=0.

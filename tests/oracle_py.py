@@ -85,6 +85,9 @@ class Oracle:
         L.orc_bm_rtl.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(BmRtlParams), i16p]
         L.orc_bm_rtl_last_sat_events.restype = ctypes.c_int64
         L.orc_bm_cv.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(BmCvParams), i16p]
+        L.orc_bm_cv_cost.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(BmCvParams), i16p, i16p]
+        L.orc_validate_disparity.argtypes = [i16p, i16p] + [ctypes.c_int] * 5
+        L.orc_filter_speckles.argtypes = [i16p] + [ctypes.c_int] * 5
         L.orc_reproject.argtypes = [i16p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
                                     ctypes.POINTER(ctypes.c_float)]
@@ -166,6 +169,23 @@ class Oracle:
         rc = self.L.orc_bm_cv(lp, rp, W, H, ctypes.byref(p), disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
         if rc != 0:
             raise ValueError(f"orc_bm_cv rc={rc}")
+        return disp
+
+    def bm_cv_post(self, pl, pr, wsz=21, ndisp=64, prefilter_cap=31, texture_threshold=10, uniqueness_ratio=10,
+                   disp12_max_diff=1, speckle_window=50, speckle_range=32):
+        """cv::StereoBM as configured at main.cpp:198-212: BM, then validateDisparity, then filterSpeckles."""
+        pl, lp = _u8(pl); pr, rp = _u8(pr)
+        H, W = pl.shape
+        p = BmCvParams(wsz, ndisp, prefilter_cap, texture_threshold, uniqueness_ratio)
+        disp = np.empty((H, W), np.int16); cost = np.zeros((H, W), np.int16)
+        i16p = ctypes.POINTER(ctypes.c_int16)
+        rc = self.L.orc_bm_cv_cost(lp, rp, W, H, ctypes.byref(p), disp.ctypes.data_as(i16p), cost.ctypes.data_as(i16p))
+        if rc != 0:
+            raise ValueError(f"orc_bm_cv_cost rc={rc}")
+        if disp12_max_diff >= 0:
+            self.L.orc_validate_disparity(disp.ctypes.data_as(i16p), cost.ctypes.data_as(i16p), W, H, 0, ndisp, disp12_max_diff)
+        if speckle_window > 0 and speckle_range >= 0:
+            self.L.orc_filter_speckles(disp.ctypes.data_as(i16p), W, H, -16, speckle_window, speckle_range)
         return disp
 
     def reproject(self, disp, P_l, P_r, decim=1, apply_local=0):

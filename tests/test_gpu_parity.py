@@ -337,3 +337,30 @@ def test_c5_slam_loop_octomap(u, oracle, tmp_path):
     assert int(got["finite_points"]) == finite
     assert abs(int(got["inserted"]) - inserted) <= 2                  # float sqrt at exactly the 25 m gate
     assert abs(float(got["checksum"]) - checksum) <= 1e-6 * abs(checksum) + 200.0
+
+
+def test_opencv_postfilters(u, fe640, golden, cv_golden, oracle):
+    """SURVEY 8f row 1: cv::StereoBM exactly as configured at main.cpp:198-212 (validateDisparity + filterSpeckles)."""
+    fe640.set_bm_params(width=640, height=480, profile=u.PROFILE_OPENCV, num_disparities=64, block_size=21, texture_threshold=10,
+                        uniqueness_ratio=10, prefilter_cap=31, min_disparity=0, disp12_max_diff=1, speckle_window_size=50, speckle_range=32)
+    fe640.submit_rect(0, golden["rect_l"], golden["rect_r"]); b = fe640.wait()
+    got = fe640.receive_disp(b)[0]
+    assert np.array_equal(got, cv_golden["maincpp_postfilter"])          # cv2.StereoBM on the reference's bundled pair
+    L, R = u.synth_batch(1, 3, 3, 640, 480, 64)
+    for d12, sw, sr in ((1, 0, 0), (-1, 50, 32), (2, 120, 16), (0, 30, 48)):
+        fe640.set_bm_params(disp12_max_diff=d12, speckle_window_size=sw, speckle_range=sr, block_size=15)
+        fe640.submit_rect(1, L, R); b = fe640.wait()
+        got = fe640.receive_disp(b)
+        for i in (0, 2):
+            want = oracle.bm_cv_post(oracle.xsobel_cv(L[i]), oracle.xsobel_cv(R[i]), wsz=15, ndisp=64, disp12_max_diff=d12,
+                                     speckle_window=sw, speckle_range=sr)
+            assert np.array_equal(got[i], want), (d12, sw, sr, i, int((got[i] != want).sum()))
+    fe640.set_bm_params(disp12_max_diff=-1, speckle_window_size=0, speckle_range=0)
+
+
+def test_stereobm_facade_maincpp_configuration(u, golden, cv_golden):
+    bm = u.StereoBM.create(16, 9)                                         # main.cpp:201
+    bm.setPreFilterCap(31); bm.setBlockSize(21); bm.setMinDisparity(0); bm.setNumDisparities(64)
+    bm.setTextureThreshold(10); bm.setUniquenessRatio(10)
+    bm.setSpeckleWindowSize(50); bm.setSpeckleRange(32); bm.setDisp12MaxDiff(1)
+    assert np.array_equal(bm.compute(golden["rect_l"], golden["rect_r"]), cv_golden["maincpp_postfilter"])

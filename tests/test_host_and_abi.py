@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(libpath):
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
     lib.u96_abi_version.restype = ctypes.c_int
-    assert lib.u96_abi_version() == 1
+    assert lib.u96_abi_version() == 2
     lib.u96_strerror.restype = ctypes.c_char_p
     assert b"fallback" in lib.u96_strerror(-6)
 
@@ -50,7 +50,7 @@ def test_product_does_not_touch_oracle():
 
 def test_params_struct_layout():
     from u96_slam_b200.stereo import BmParams, RectParams
-    assert ctypes.sizeof(BmParams) == 14 * 4
+    assert ctypes.sizeof(BmParams) == 17 * 4
     assert ctypes.sizeof(RectParams) == (4 + 2 + 2 + 2 + 18) * 4
     p = RectParams.from_dict(__import__("u96_slam_b200").SHIPPED_RECT_PARAMS)
     assert p.f[1][0] == 39609530 and p.rot[1][2][2] == 16568783 and p.c2_f2[1] == 5932596

@@ -161,3 +161,26 @@ def test_reproject_matches_float_formula(oracle):
         assert np.array_equal(out[..., 2][~bad], Z[~bad]) and np.array_equal(out[..., 0][~bad], X[~bad])
         loc = oracle.reproject(disp, P_l, P_r, decim, 1)
         assert np.array_equal(loc[..., 0][~bad], out[..., 2][~bad]) and np.array_equal(loc[..., 1][~bad], -out[..., 0][~bad])
+
+
+def test_postfilters_match_opencv_public_functions(oracle, golden, cv_golden):
+    """f1 row: validateDisparity + filterSpeckles as cv::StereoBM::compute applies them (main.cpp:210-212)."""
+    cv2 = pytest.importorskip("cv2")
+    import ctypes
+    from oracle_py import BmCvParams
+    pl, pr = oracle.xsobel_cv(golden["rect_l"], 31), oracle.xsobel_cv(golden["rect_r"], 31)
+    # (a) the reference's exact configuration on the reference's bundled pair: bit-exact vs cv2.StereoBM
+    assert np.array_equal(oracle.bm_cv_post(pl, pr), cv_golden["maincpp_postfilter"])
+    # (b) the two filters against OpenCV's public functions on the same inputs
+    H, W = pl.shape
+    p = BmCvParams(21, 64, 31, 10, 10)
+    disp = np.empty((H, W), np.int16); cost = np.zeros((H, W), np.int16)
+    i16p, u8p = ctypes.POINTER(ctypes.c_int16), ctypes.POINTER(ctypes.c_uint8)
+    oracle.L.orc_bm_cv_cost(pl.ctypes.data_as(u8p), pr.ctypes.data_as(u8p), W, H, ctypes.byref(p), disp.ctypes.data_as(i16p), cost.ctypes.data_as(i16p))
+    mine = disp.copy(); oracle.L.orc_validate_disparity(mine.ctypes.data_as(i16p), cost.ctypes.data_as(i16p), W, H, 0, 64, 1)
+    theirs = disp.copy(); cv2.validateDisparity(theirs, cost, 0, 64, 1)
+    assert np.array_equal(mine, theirs) and (mine != disp).sum() > 1000
+    for size, diff in ((50, 32), (200, 16), (10, 64)):
+        a = disp.copy(); oracle.L.orc_filter_speckles(a.ctypes.data_as(i16p), W, H, -16, size, diff)
+        b = disp.copy(); cv2.filterSpeckles(b, -16, size, diff)
+        assert np.array_equal(a, b) and (a != disp).sum() > 100

@@ -37,6 +37,7 @@ constexpr int BM_LS = 16;         // horizontal sliding segment length
 struct BmArgs {
     const uint8_t *xl, *xr;
     int16_t *disp;
+    int16_t *cost;                      // OPENCV: winning SAD of valid pixels (validateDisparity input) or null
     int pitch; size_t frame;            // input bytes
     int dpitch; size_t dframe;          // output elements
     int W, H, D, DP, NG;                // NG = DP/8 groups (last one = special lanes)
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(BM_THREADS) k_bm(const BmArgs a)
                     const int den = pp + nn - 2 * minsad + abs(pp - nn);
                     const int frac = den ? ((pp - nn) * 256) / den : 0;       // C division, toward zero
                     out = (mind * 256 + frac + 15) >> 4;
+                    if (a.cost) a.cost[(size_t)f * a.dframe + (size_t)yc * a.dpitch + ctr0 + p] = (int16_t)minsad;
                 } else out = -16;
             }
             const int xo = ctr0 + p + ((PROFILE == U96_PROFILE_RTL) ? a.x_store_offset : 0);
@@ -433,7 +435,7 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
         return 1 + launch_bm_fast(xl, xr, pitch, frame, disp, c, n, s);
     BmArgs a;
     if (!bm_fill_args(c, a)) return 1;
-    a.xl = xl; a.xr = xr; a.disp = disp.p; a.pitch = pitch; a.frame = frame;
+    a.xl = xl; a.xr = xr; a.disp = disp.p; a.cost = c.cost; a.pitch = pitch; a.frame = frame;
     a.dpitch = disp.pitch; a.dframe = disp.frame;
     const int smem = bm_smem_bytes(c);
     dim3 grid(a.ntx, a.nbands, n);

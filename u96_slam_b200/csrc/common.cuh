@@ -34,6 +34,7 @@ struct BmConfig {
     int W, H, D, wsz, profile;
     int uni_enable, uni_mode, uni_thr, x_store_offset, rtl_extended;   // RTL
     int cap, tex_thr, uniq;                                            // OPENCV
+    int16_t *cost = nullptr;                                           // OPENCV: winning SAD per valid pixel (same pitch as disp) or null
 };
 int  bm_smem_bytes(const BmConfig &c);
 int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
@@ -42,6 +43,10 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
 bool bm_fast_supported(const BmConfig &c);
 int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
                    const BmConfig &c, int n, cudaStream_t s);
+
+// cv::StereoBM post filters (OPENCV profile): validateDisparity then filterSpeckles; scratch = 2 int32 per pixel of the batch
+int launch_postfilter(Img16 disp, const int16_t *cost, int W, int H, int n, int ndisp, int disp12_max_diff,
+                      int speckle_window, int speckle_range, int *scratch, cudaStream_t s);
 
 int launch_reproject(const int16_t *disp, int dpitch, size_t dframe, int W, int H, int n,
                      const double *P_l, const double *P_r, int decim, int flags, float *xyz, cudaStream_t s);

@@ -31,6 +31,9 @@ enum { FROM_RAW = 0, FROM_RECT = 1, FROM_XSBL = 2 };
 struct Bank {
     uint8_t *raw[2] = {nullptr, nullptr}, *rect[2] = {nullptr, nullptr}, *xsbl[2] = {nullptr, nullptr};
     int16_t *disp = nullptr;
+    int16_t *cost = nullptr;            // OPENCV post filters: winning SAD per pixel (lazy)
+    int *cc = nullptr;                  // filterSpeckles: label + size, 2 int32 per pixel of a batch (lazy, per bank)
+    size_t cc_cap = 0;
     // where the current contents of each stage live (internal buffer or a caller's device pointer)
     const uint8_t *cur_raw[2] = {nullptr, nullptr}, *cur_rect[2] = {nullptr, nullptr}, *cur_xsbl[2] = {nullptr, nullptr};
     int raw_pitch = 0, rect_pitch = 0, xsbl_pitch = 0;
@@ -80,6 +83,7 @@ static int validate_bm(const u96_handle *h, const u96_bm_params &p)
         if (p.num_disparities < 16 || p.num_disparities > 256 || (p.num_disparities & 15)) return U96_ERR_INVALID;
         if (p.prefilter_cap < 1 || p.prefilter_cap > 63) return U96_ERR_INVALID;
         if (p.uniqueness_ratio < 0 || p.texture_threshold < 0) return U96_ERR_INVALID;
+        if (p.speckle_window_size < 0 || p.speckle_window_size > 1000000) return U96_ERR_INVALID;
         if (p.width - p.num_disparities + 1 - 2 * hw <= 0) return U96_ERR_INVALID;
         max_ad = 2 * p.prefilter_cap;
     } else return U96_ERR_INVALID;
@@ -154,6 +158,7 @@ int u96_create(u96_handle **out, int device, int max_w, int max_h, int max_batch
     u96_bm_params d{};
     d.width = max_w; d.height = max_h; d.block_size = 21; d.num_disparities = 64; d.prefilter_cap = 31;
     d.uniqueness_ratio = 10; d.texture_threshold = 10; d.profile = U96_PROFILE_RTL; d.x_store_offset = 1;
+    d.disp12_max_diff = -1; d.speckle_window_size = 0; d.speckle_range = 0;
     h->bm = d;
     *out = h;
     return U96_OK;
@@ -168,6 +173,8 @@ void u96_destroy(u96_handle *h)
         if (k.stream) cudaStreamSynchronize(k.stream);
         for (int i = 0; i < 2; i++) { cudaFree(k.raw[i]); cudaFree(k.rect[i]); cudaFree(k.xsbl[i]); }
         cudaFree(k.disp);
+        cudaFree(k.cost);
+        cudaFree(k.cc);
         if (k.done) cudaEventDestroy(k.done);
         for (int i = 0; i < 5; i++) if (k.ev[i]) cudaEventDestroy(k.ev[i]);
         for (int i = 0; i < 3; i++) { if (k.sub_ev[i]) cudaEventDestroy(k.sub_ev[i]); if (k.sub[i]) { cudaStreamSynchronize(k.sub[i]); cudaStreamDestroy(k.sub[i]); } }
@@ -272,8 +279,17 @@ static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStrea
         h->launches += launch_xsobel(k.cur_rect[0] + (size_t)f0 * k.rect_frame, k.cur_rect[1] + (size_t)f0 * k.rect_frame, k.rect_pitch,
                                      k.rect_frame, xsblL, xsblR, W, H, nf, h->bm.profile, h->bm.prefilter_cap, s);
     if (prof) CK(cudaEventRecord(k.ev[3], s));
+    BmConfig cfg = bm_config(h->bm);
+    const bool cv = (h->bm.profile == U96_PROFILE_OPENCV);
+    const bool want_validate = cv && h->bm.disp12_max_diff >= 0;
+    const bool want_speckle = cv && h->bm.speckle_window_size > 0 && h->bm.speckle_range >= 0;
+    if (want_validate) cfg.cost = k.cost + o;
     h->launches += launch_bm(k.cur_xsbl[0] + (size_t)f0 * k.xsbl_frame, k.cur_xsbl[1] + (size_t)f0 * k.xsbl_frame, k.xsbl_pitch,
-                             k.xsbl_frame, disp, bm_config(h->bm), nf, s);
+                             k.xsbl_frame, disp, cfg, nf, s);
+    if (want_validate || want_speckle)                       // cv::StereoBM::compute post filters (main.cpp:210-212)
+        h->launches += launch_postfilter(disp, want_validate ? k.cost + o : nullptr, W, H, nf, h->bm.num_disparities,
+                                         want_validate ? h->bm.disp12_max_diff : -1, want_speckle ? h->bm.speckle_window_size : 0,
+                                         h->bm.speckle_range, want_speckle ? k.cc + (size_t)2 * f0 * W * H : nullptr, s);
     if (prof) CK(cudaEventRecord(k.ev[4], s));
     return U96_OK;
 }
@@ -313,6 +329,17 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     if (from <= FROM_RECT) { k.cur_xsbl[0] = k.xsbl[0]; k.cur_xsbl[1] = k.xsbl[1]; k.xsbl_pitch = pitch; k.xsbl_frame = frame; }
     else { k.cur_xsbl[0] = cur[0]; k.cur_xsbl[1] = cur[1]; k.xsbl_pitch = cur_pitch; k.xsbl_frame = cur_frame; }
 
+    if (h->bm.profile == U96_PROFILE_OPENCV && h->bm.disp12_max_diff >= 0 && !k.cost) {
+        if (cudaMalloc(&k.cost, (size_t)pitch * H * h->maxB * sizeof(int16_t)) != cudaSuccess) return U96_ERR_NOMEM;
+    }
+    if (h->bm.profile == U96_PROFILE_OPENCV && h->bm.speckle_window_size > 0) {
+        const size_t need = (size_t)2 * n * W * H;
+        if (need > k.cc_cap) {                                // the bank is idle here (not pending)
+            cudaFree(k.cc); k.cc = nullptr; k.cc_cap = 0;
+            if (cudaMalloc(&k.cc, need * sizeof(int)) != cudaSuccess) return U96_ERR_NOMEM;
+            k.cc_cap = need;
+        }
+    }
     const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= 64;
     if (!pipelined) {
         if (!zero_copy)

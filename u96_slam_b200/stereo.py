@@ -37,7 +37,7 @@ class BmParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "width", "height", "block_size", "num_disparities", "min_disparity", "prefilter_cap",
         "uniqueness_ratio", "texture_threshold", "profile", "uni_enable", "uni_mode", "uni_thr",
-        "x_store_offset", "rtl_extended")]
+        "x_store_offset", "rtl_extended", "disp12_max_diff", "speckle_window_size", "speckle_range")]
 
 
 class RectParams(ctypes.Structure):
@@ -338,7 +338,8 @@ class StereoBM:
 
     def __init__(self, numDisparities=64, blockSize=21, device=0):
         self.p = dict(num_disparities=numDisparities, block_size=blockSize, prefilter_cap=31, texture_threshold=10,
-                      uniqueness_ratio=15, min_disparity=0, profile=PROFILE_OPENCV)
+                      uniqueness_ratio=15, min_disparity=0, profile=PROFILE_OPENCV, disp12_max_diff=-1,
+                      speckle_window_size=0, speckle_range=0)
         self.device, self.fe, self._shape = device, None, None
 
     @classmethod
@@ -351,6 +352,9 @@ class StereoBM:
     def setNumDisparities(self, v): self.p["num_disparities"] = v
     def setTextureThreshold(self, v): self.p["texture_threshold"] = v
     def setUniquenessRatio(self, v): self.p["uniqueness_ratio"] = v
+    def setSpeckleWindowSize(self, v): self.p["speckle_window_size"] = v
+    def setSpeckleRange(self, v): self.p["speckle_range"] = v
+    def setDisp12MaxDiff(self, v): self.p["disp12_max_diff"] = v
 
     def compute(self, left, right):
         left = np.asarray(left)
