@@ -25,8 +25,12 @@ static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 struct RectMapParams { u96_rect_params p; int W, H; int wrap16; };
 
 int launch_rect_build_map(const RectMapParams &rp, int2 *map /*[2][H][W]*/, cudaStream_t s);
+// per-parameter-set plan of the TMA remap path: source bounding boxes of the destination tiles
+struct RectPlan { bool tma = false; int BW = 0, BH = 0, stage_bytes = 0, tiles_x = 0, tiles_y = 0; int4 *d_tiles = nullptr; };
+int rect_plan_build(RectPlan &pl, const int2 *map, int W, int H, cudaStream_t s);
+void rect_plan_free(RectPlan &pl);
 int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
-                      Img8 dstL, Img8 dstR, const int2 *map, int W, int H, int n, cudaStream_t s);
+                      Img8 dstL, Img8 dstR, const int2 *map, const RectPlan &pl, int W, int H, int n, cudaStream_t s);
 int launch_xsobel(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
                   Img8 dstL, Img8 dstR, int W, int H, int n, int profile, int cap, cudaStream_t s);
 

@@ -8,6 +8,12 @@
 // and the per-frame kernel is a pure gather: 1 B/px read + 1 B/px written to HBM.
 // The FPGA's run-length command stream (fpga.c:368-605) is a line-buffer scheduling
 // artefact and has no GPU counterpart: every destination pixel is written exactly once.
+#include <cuda.h>      // CUtensorMap types; cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint (no -lcuda)
+
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace u96 {
@@ -189,9 +195,258 @@ __global__ void __launch_bounds__(128, 8) k_rect_remap(const uint8_t *__restrict
     }
 }
 
-int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
-                      Img8 dstL, Img8 dstR, const int2 *map, int W, int H, int n, cudaStream_t s)
+// ---------------------------------------------------------------------------------------------
+// TMA path.  The map is frame-invariant, so the SOURCE bounding box of every 128x16 destination tile
+// is known once the map exists (k_rect_tile_bbox).  Per frame a tile then needs one fixed-size box of
+// the source image: a producer warp streams those boxes into a 4-stage shared-memory ring with
+// cp.async.bulk.tensor (3-D tensor map x, y, frame; the hardware zero-fills everything outside the
+// image = the "taps outside the source read 0" rule), 8 consumer warps interpolate out of shared
+// memory with the same word/dp4a arithmetic as above and write 128-byte row segments.  HBM sees each
+// source byte once (neighbouring tiles' halo overlap is absorbed by L2) and each destination byte once.
+constexpr int RT_TW = 128, RT_TH = 16, RT_STAGES = 4, RT_CONS = 256, RT_THREADS = RT_CONS + 32, RT_G = RT_TH / 8;
+
+__global__ void __launch_bounds__(256) k_rect_tile_bbox(const int2 *__restrict__ map, int4 *__restrict__ tiles, int W, int H, int tiles_x, int ntiles)
 {
+    __shared__ int s_mm[4];
+    const int tile = blockIdx.x, cam = blockIdx.y;
+    const int tx0 = (tile % tiles_x) * RT_TW, ty0 = (tile / tiles_x) * RT_TH;
+    if (threadIdx.x == 0) { s_mm[0] = INT_MAX; s_mm[1] = INT_MAX; s_mm[2] = INT_MIN; s_mm[3] = INT_MIN; }
+    __syncthreads();
+    int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
+    for (int i = threadIdx.x; i < RT_TW * RT_TH; i += blockDim.x) {
+        const int x = tx0 + (i % RT_TW), y = ty0 + (i / RT_TW);
+        if (x < W && y < H) {
+            const int2 e = map[((size_t)cam * H + y) * W + x];
+            const int xi = e.x >> 5, yi = e.y >> 5;
+            x0 = min(x0, xi); x1 = max(x1, xi + 1); y0 = min(y0, yi); y1 = max(y1, yi + 1);
+        }
+    }
+    atomicMin(&s_mm[0], x0); atomicMin(&s_mm[1], y0); atomicMax(&s_mm[2], x1); atomicMax(&s_mm[3], y1);
+    __syncthreads();
+    // the box origin is rounded down to a 16-byte boundary: TMA needs 16-byte aligned global row starts
+    if (threadIdx.x == 0) tiles[(size_t)cam * ntiles + tile] = make_int4(s_mm[0] & ~15, s_mm[1], s_mm[2], s_mm[3]);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+// words of one 4-pixel group out of the shared-memory box (same arithmetic as remap_words)
+template <int ROWS>
+__device__ __forceinline__ uint32_t remap_group_smem(const uint32_t *w, int bww, uint32_t mis, const uint32_t (&selw)[4],
+                                                     const uint32_t (&wx)[4], const uint32_t (&wy)[4][3])
+{
+    uint32_t lo[ROWS], hi[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        const uint32_t a0 = w[r * bww], a1 = w[r * bww + 1], a2 = w[r * bww + 2];
+        lo[r] = __funnelshift_r(a0, a1, mis);
+        hi[r] = __funnelshift_r(a1, a2, mis);
+    }
+    uint32_t acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        acc[k] = 1u << 15;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) acc[k] += __dp4a(__byte_perm(lo[r], hi[r], selw[k]), wx[k], 0u) * wy[k][r];
+    }
+    const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
+    return __byte_perm(p01, p23, 0x5410);
+}
+
+__global__ void __launch_bounds__(RT_THREADS) k_rect_remap_tma(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+                                                               uint8_t *__restrict__ dL, uint8_t *__restrict__ dR, int dp, size_t df,
+                                                               const int2 *__restrict__ map, const int4 *__restrict__ tiles,
+                                                               int W, int H, int n, int BW, int BH, int stage_bytes, int tiles_x, int ntiles, int fpb)
+{
+    extern __shared__ __align__(128) uint8_t rt_smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(rt_smem + (size_t)RT_STAGES * stage_bytes);
+    uint64_t *empty = full + RT_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, cam = blockIdx.y;
+    const int f0 = blockIdx.z * fpb, nf = min(fpb, n - f0);
+    const int4 tb = tiles[(size_t)cam * ntiles + tile];
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < RT_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], RT_CONS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == RT_CONS / 32) {
+        // ---- producer: one lane streams the per-frame source boxes through the ring ----
+        if (lane == 0) {
+            const CUtensorMap *tm = cam ? &tmR : &tmL;
+            for (int f = 0; f < nf; f++) {
+                const int s = f % RT_STAGES, k = f / RT_STAGES;
+                if (k > 0) mbar_wait(&empty[s], (uint32_t)(k - 1) & 1u);
+                mbar_expect_tx(&full[s], (uint32_t)(BW * BH));
+                tma_load_3d(rt_smem + (size_t)s * stage_bytes, tm, tb.x, tb.y, f0 + f, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: thread = (row r, 4-pixel group) x RT_G rows ----
+    const int tx0 = (tile % tiles_x) * RT_TW, ty0 = (tile / tiles_x) * RT_TH;
+    const int x4 = tx0 + lane * 4;
+    const int bww = BW >> 2;
+    int mode[RT_G];                    // 0 dead, 2/3 word path with that many rows, 1 generic
+    int o0[RT_G];
+    uint32_t mis[RT_G], selw[RT_G][4], wx[RT_G][4], wy[RT_G][4][3];
+    size_t doff[RT_G];
+#pragma unroll
+    for (int g = 0; g < RT_G; g++) {
+        const int y = ty0 + warp + 8 * g;
+        const bool live = (x4 < W) && (y < H);
+        doff[g] = (size_t)y * dp + x4;
+        int xi[4], yi[4], xf[4], yf[4];
+        const int2 *m = map + ((size_t)cam * H + (live ? y : 0)) * W + (live ? x4 : 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // pixels right of the image inside the last 4-group repeat the group's first entry (never stored past the pitch)
+            const int2 e = live ? m[(x4 + k < W) ? k : 0] : make_int2(0, 0);
+            xi[k] = (e.x >> 5) - tb.x; xf[k] = e.x & 31; yi[k] = (e.y >> 5) - tb.y; yf[k] = e.y & 31;
+        }
+        int ymin = yi[0], ymax = yi[0];
+#pragma unroll
+        for (int k = 1; k < 4; k++) { ymin = min(ymin, yi[k]); ymax = max(ymax, yi[k]); }
+        bool words = live && (ymax - ymin <= 1);
+#pragma unroll
+        for (int k = 1; k < 4; k++) words = words && (xi[k] >= xi[0]) && (xi[k] - xi[0] <= 6);
+        const bool three = words && (ymax != ymin);
+        const unsigned any3 = __any_sync(0xFFFFFFFFu, three);
+        mode[g] = !live ? 0 : words ? (any3 ? 3 : 2) : 1;
+        o0[g] = ymin * BW + xi[0];
+        mis[g] = (uint32_t)(o0[g] & 3) * 8u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t dk = (uint32_t)(xi[k] - xi[0]) & 7u;
+            selw[g][k] = dk | ((dk + 1) << 4);
+            wx[g][k] = (uint32_t)(32 - xf[k]) | ((uint32_t)xf[k] << 8);
+            const uint32_t a = 64u * (uint32_t)(32 - yf[k]), b = 64u * (uint32_t)yf[k];
+            const bool up = (yi[k] == ymin);
+            wy[g][k][0] = up ? a : 0u; wy[g][k][1] = up ? b : a; wy[g][k][2] = up ? 0u : b;
+        }
+    }
+    uint8_t *dbase = (cam ? dR : dL) + (size_t)f0 * df;
+    for (int f = 0; f < nf; f++) {
+        const int s = f % RT_STAGES, kk = f / RT_STAGES;
+        mbar_wait(&full[s], (uint32_t)kk & 1u);
+        const uint8_t *sb = rt_smem + (size_t)s * stage_bytes;
+        uint32_t out[RT_G];
+#pragma unroll
+        for (int g = 0; g < RT_G; g++) {
+            out[g] = 0;
+            if (mode[g] >= 2) {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(sb) + (o0[g] >> 2);
+                out[g] = (mode[g] == 3) ? remap_group_smem<3>(w, bww, mis[g], selw[g], wx[g], wy[g])
+                                        : remap_group_smem<2>(w, bww, mis[g], selw[g], wx[g], wy[g]);
+            } else if (mode[g] == 1) {
+                // generic path (exotic maps): byte gathers; every tap lies inside the box, outside-image taps are TMA zero fill
+                const int y = ty0 + warp + 8 * g;
+                const int2 *m = map + ((size_t)cam * H + y) * W + x4;
+                for (int k = 0; k < 4; k++) {
+                    const int2 e = m[(x4 + k < W) ? k : 0];
+                    const int xi = (e.x >> 5) - tb.x, yi = (e.y >> 5) - tb.y, xf = e.x & 31, yf = e.y & 31;
+                    const uint8_t *t = sb + yi * BW + xi;
+                    const uint32_t sum = t[0] * (uint32_t)((32 - xf) * (32 - yf)) + t[1] * (uint32_t)(xf * (32 - yf)) +
+                                         t[BW] * (uint32_t)((32 - xf) * yf) + t[BW + 1] * (uint32_t)(xf * yf);
+                    out[g] |= min(255u, ((sum >> 9) + 1u) >> 1) << (8 * k);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);           // this warp is done with the stage
+        uint8_t *d = dbase + (size_t)f * df;
+#pragma unroll
+        for (int g = 0; g < RT_G; g++)
+            if (mode[g]) *reinterpret_cast<uint32_t *>(d + doff[g]) = out[g];
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled tmap_encoder()
+{
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// Source bounding boxes of the destination tiles; decides whether the TMA path applies to this parameter set.
+int rect_plan_build(RectPlan &pl, const int2 *map, int W, int H, cudaStream_t s)
+{
+    pl.tma = false;
+    pl.tiles_x = (W + RT_TW - 1) / RT_TW; pl.tiles_y = (H + RT_TH - 1) / RT_TH;
+    const int nt = pl.tiles_x * pl.tiles_y;
+    if (cudaMalloc(&pl.d_tiles, sizeof(int4) * 2 * nt) != cudaSuccess) { pl.d_tiles = nullptr; return 0; }
+    k_rect_tile_bbox<<<dim3(nt, 2), 256, 0, s>>>(map, pl.d_tiles, W, H, pl.tiles_x, nt);
+    int4 *ht = new int4[2 * nt];
+    if (cudaMemcpyAsync(ht, pl.d_tiles, sizeof(int4) * 2 * nt, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { delete[] ht; return 1; }
+    int bw = 0, bh = 0;
+    for (int i = 0; i < 2 * nt; i++) { bw = std::max(bw, ht[i].z - ht[i].x + 1); bh = std::max(bh, ht[i].w - ht[i].y + 1); }
+    delete[] ht;
+    pl.BW = align_up(bw, 16); pl.BH = bh;
+    pl.stage_bytes = align_up(pl.BW * (pl.BH + 1) + 16, 128);     // one spare row + tail for the word path's over-read
+    pl.tma = (pl.BW <= 256 && pl.BH <= 255 && pl.stage_bytes <= 16384 && tmap_encoder() != nullptr && !getenv("U96_RECT_LEGACY"));
+    return 1;
+}
+
+void rect_plan_free(RectPlan &pl) { cudaFree(pl.d_tiles); pl.d_tiles = nullptr; pl.tma = false; }
+
+static bool encode_src_map(CUtensorMap *tm, const uint8_t *src, int pitch, size_t frame, int W, int H, int n, int BW, int BH)
+{
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame};
+    const cuuint32_t box[3] = {(cuuint32_t)BW, (cuuint32_t)BH, 1u};
+    const cuuint32_t es[3] = {1u, 1u, 1u};
+    return tmap_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(src), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
+                      Img8 dstL, Img8 dstR, const int2 *map, const RectPlan &pl, int W, int H, int n, cudaStream_t s)
+{
+    if (pl.tma && (src_pitch % 16 == 0) && (src_frame % 16 == 0) && (((uintptr_t)srcL | (uintptr_t)srcR) % 16 == 0)) {
+        CUtensorMap tmL, tmR;
+        if (encode_src_map(&tmL, srcL, src_pitch, src_frame, W, H, n, pl.BW, pl.BH) &&
+            encode_src_map(&tmR, srcR, src_pitch, src_frame, W, H, n, pl.BW, pl.BH)) {
+            const int nt = pl.tiles_x * pl.tiles_y;
+            const int fpb = 16;
+            const int smem = RT_STAGES * pl.stage_bytes + 2 * RT_STAGES * (int)sizeof(uint64_t);
+            cudaFuncSetAttribute(k_rect_remap_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_STAGES * 16384 + 128);
+            dim3 grid(nt, 2, (n + fpb - 1) / fpb);
+            k_rect_remap_tma<<<grid, RT_THREADS, smem, s>>>(tmL, tmR, dstL.p, dstR.p, dstL.pitch, dstL.frame, map, pl.d_tiles, W, H, n,
+                                                            pl.BW, pl.BH, pl.stage_bytes, pl.tiles_x, nt, fpb);
+            return 1;
+        }
+    }
     const int tx = 128;
     dim3 grid((((W + 3) / 4) * H + tx - 1) / tx, 2 * ((n + RECT_FPB - 1) / RECT_FPB));
     k_rect_remap<<<grid, tx, 0, s>>>(srcL, srcR, src_pitch, src_frame, dstL.p, dstR.p, dstL.pitch, dstL.frame, map, W, H, n);

@@ -55,6 +55,7 @@ struct u96_handle {
     u96_rect_params rect{};
     bool rect_set = false, map_valid = false;
     int2 *map = nullptr;
+    RectPlan plan;
     Bank bank[2];
     std::deque<int> fifo;
     cudaStream_t user_stream = nullptr;
@@ -181,6 +182,7 @@ void u96_destroy(u96_handle *h)
         if (k.stream) cudaStreamDestroy(k.stream);
     }
     cudaFree(h->map);
+    rect_plan_free(h->plan);
     cudaFree(h->xyz);
     delete h;
 }
@@ -257,6 +259,8 @@ static int ensure_map(u96_handle *h, cudaStream_t s)
     rp.p = h->rect; rp.W = h->bm.width; rp.H = h->bm.height;
     rp.wrap16 = (rp.W <= 1023 && rp.H <= 511) ? 1 : 0;      // RTL counter widths; beyond = RTL-extended
     h->launches += launch_rect_build_map(rp, h->map, s);
+    rect_plan_free(h->plan);
+    h->launches += rect_plan_build(h->plan, h->map, rp.W, rp.H, s);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));                             // other bank's stream may use the map next
     h->map_valid = true;
@@ -273,7 +277,7 @@ static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStrea
     const Img16 disp{k.disp + o, pitch, frame};
     if (from == FROM_RAW)
         h->launches += launch_rect_remap(k.cur_raw[0] + (size_t)f0 * k.raw_frame, k.cur_raw[1] + (size_t)f0 * k.raw_frame, k.raw_pitch,
-                                         k.raw_frame, rectL, rectR, h->map, W, H, nf, s);
+                                         k.raw_frame, rectL, rectR, h->map, h->plan, W, H, nf, s);
     if (prof) CK(cudaEventRecord(k.ev[2], s));
     if (from <= FROM_RECT)
         h->launches += launch_xsobel(k.cur_rect[0] + (size_t)f0 * k.rect_frame, k.cur_rect[1] + (size_t)f0 * k.rect_frame, k.rect_pitch,

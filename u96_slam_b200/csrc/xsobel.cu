@@ -27,89 +27,100 @@ __device__ __forceinline__ void vsum4(uint32_t a, uint32_t b, uint32_t c, uint32
     hi = ah + 2u * bh + ch;
 }
 
+// One thread = 16 pixels x XS_R consecutive rows: the XS_R+2 input rows are all requested before any
+// arithmetic (enough bytes in flight per SM to cover the HBM latency, each row fetched 1.5x instead of 3x),
+// then a rolling window of three widened rows produces the outputs.
+constexpr int XS_R = 4;
+
 template <int PROFILE>
 __global__ void __launch_bounds__(256) k_xsobel(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR, int sp, size_t sf,
                                                 uint8_t *__restrict__ dL, uint8_t *__restrict__ dR, int dp, size_t df,
                                                 int W, int H, int cap)
 {
     const int w16 = (W + 15) >> 4;
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;       // flattened (row, 16-pixel group)
-    if (item >= w16 * H) return;
-    const int y = item / w16;
-    const int x0 = (item - y * w16) * 16;
+    const int nrg = (H + XS_R - 1) / XS_R;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;       // flattened (row group, 16-pixel group)
+    if (item >= w16 * nrg) return;
+    const int rg = item / w16;
+    const int x0 = (item - rg * w16) * 16;
+    const int y0 = rg * XS_R;
     const int lr = blockIdx.y & 1, f = blockIdx.y >> 1;
-    const uint8_t *src = (lr ? srcR : srcL) + (size_t)f * sf;
-    uint8_t *dst = (lr ? dR : dL) + (size_t)f * df + (size_t)y * dp + x0;
+    const uint8_t *src = (lr ? srcR : srcL) + (size_t)f * sf + x0;
+    uint8_t *dst = (lr ? dR : dL) + (size_t)f * df + (size_t)y0 * dp + x0;
 
-    int ym, yp;
-    uint32_t border, lo_off, hi_lim;     // clamp to [lo_off, hi_lim] after adding the bias
-    if (PROFILE == U96_PROFILE_RTL) {
-        if (y == 0 || y == H - 1) {      // invalid lines
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
-            return;
-        }
-        ym = y - 1; yp = y + 1;
-        border = 32;
-    } else {
-        if ((H & 1) && y == H - 1) {
-            const uint32_t c4 = (uint32_t)cap * 0x01010101u;
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(c4, c4, c4, c4);
-            return;
-        }
-        ym = (y > 0) ? y - 1 : 1;        // reflect-101
-        yp = (y < H - 1) ? y + 1 : H - 2;
-        border = (uint32_t)cap;
-    }
-    // s + BIAS, BIAS = 1024 + off keeps both halves positive (|s| <= 1020)
-    const uint32_t off = (PROFILE == U96_PROFILE_RTL) ? 32u : (uint32_t)cap;
-    const uint32_t bias = (1024u + off) * 0x00010001u;
-    lo_off = 1024u * 0x00010001u;                                       // value 0 after clamp
-    hi_lim = (1024u + ((PROFILE == U96_PROFILE_RTL) ? 63u : 2u * (uint32_t)cap)) * 0x00010001u;
-
-    const uint8_t *ra = src + (size_t)ym * sp + x0, *rb = src + (size_t)y * sp + x0, *rc = src + (size_t)yp * sp + x0;
-    const uint4 a = *reinterpret_cast<const uint4 *>(ra), b = *reinterpret_cast<const uint4 *>(rb), c = *reinterpret_cast<const uint4 *>(rc);
+    const uint32_t border = (PROFILE == U96_PROFILE_RTL) ? 32u : (uint32_t)cap;
+    // s + BIAS, BIAS = 1024 + off keeps both halves positive (|s| <= 1020); clamp to [lo_off, hi_lim] afterwards
+    const uint32_t bias = (1024u + border) * 0x00010001u;
+    const uint32_t lo_off = 1024u * 0x00010001u;                                       // value 0 after clamp
+    const uint32_t hi_lim = (1024u + ((PROFILE == U96_PROFILE_RTL) ? 63u : 2u * (uint32_t)cap)) * 0x00010001u;
     // neighbours left of x0 and right of x0+15 (clamped addresses; the border columns are overwritten below)
     const int xl = (x0 > 0) ? -1 : 0, xr = (x0 + 16 < W) ? 16 : 15;
-    const uint32_t vl = (uint32_t)ra[xl] + 2u * rb[xl] + rc[xl];
-    const uint32_t vr = (uint32_t)ra[xr] + 2u * rb[xr] + rc[xr];
 
-    uint32_t v[10];      // v[0] = (-, px-1) ; v[1..8] = pairs (px0,px1)...(px14,px15) ; v[9] = (px16, -)
-    v[0] = vl << 16;
-    vsum4(a.x, b.x, c.x, v[1], v[2]);
-    vsum4(a.y, b.y, c.y, v[3], v[4]);
-    vsum4(a.z, b.z, c.z, v[5], v[6]);
-    vsum4(a.w, b.w, c.w, v[7], v[8]);
-    v[9] = vr;
-    uint32_t o[4];
+    uint4 row[XS_R + 2];
+    uint32_t nl[XS_R + 2], nr[XS_R + 2];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint32_t r2[2];
+    for (int j = 0; j < XS_R + 2; j++) {
+        const int yy = y0 - 1 + j;
+        int r;
+        if (PROFILE == U96_PROFILE_RTL) r = min(max(yy, 0), H - 1);                    // rows 0 / H-1 are not outputs
+        else r = (yy < 0) ? 1 : (yy == H) ? H - 2 : min(yy, H - 1);                    // reflect-101
+        const uint8_t *p = src + (size_t)r * sp;
+        row[j] = *reinterpret_cast<const uint4 *>(p);
+        nl[j] = p[xl]; nr[j] = p[xr];
+    }
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int i = 1 + 2 * q + k;                           // pair (x, x+1)
-            const uint32_t nxt = prmt(v[i], v[i + 1], 0x5432);     // (x+1, x+2)
-            const uint32_t prv = prmt(v[i - 1], v[i], 0x5432);     // (x-1, x)
-            uint32_t t = nxt + bias - prv;                         // s + off + 1024 per half, no borrow
-            t = __vmaxu2(t, lo_off);
-            t = __vminu2(t, hi_lim);
-            r2[k] = t;
+    for (int i = 0; i < XS_R; i++) {
+        const int y = y0 + i;
+        if (y >= H) break;
+        uint4 o4;
+        if (PROFILE == U96_PROFILE_RTL && (y == 0 || y == H - 1)) o4 = make_uint4(0, 0, 0, 0);       // invalid lines
+        else if (PROFILE == U96_PROFILE_OPENCV && (H & 1) && y == H - 1) {
+            const uint32_t c4 = (uint32_t)cap * 0x01010101u;
+            o4 = make_uint4(c4, c4, c4, c4);
+        } else {
+            const uint4 a = row[i], b = row[i + 1], c = row[i + 2];
+            uint32_t v[10];      // v[0] = (-, px-1) ; v[1..8] = pairs (px0,px1)...(px14,px15) ; v[9] = (px16, -)
+            v[0] = (nl[i] + 2u * nl[i + 1] + nl[i + 2]) << 16;
+            vsum4(a.x, b.x, c.x, v[1], v[2]);
+            vsum4(a.y, b.y, c.y, v[3], v[4]);
+            vsum4(a.z, b.z, c.z, v[5], v[6]);
+            vsum4(a.w, b.w, c.w, v[7], v[8]);
+            v[9] = nr[i] + 2u * nr[i + 1] + nr[i + 2];
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t r2[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int ii = 1 + 2 * q + k;                          // pair (x, x+1)
+                    const uint32_t nxt = prmt(v[ii], v[ii + 1], 0x5432);   // (x+1, x+2)
+                    const uint32_t prv = prmt(v[ii - 1], v[ii], 0x5432);   // (x-1, x)
+                    uint32_t t = nxt + bias - prv;                         // s + off + 1024 per half, no borrow
+                    t = __vmaxu2(t, lo_off);
+                    t = __vminu2(t, hi_lim);
+                    r2[k] = t;
+                }
+                o[q] = prmt(r2[0], r2[1], 0x6420);                        // low bytes: 1024 = 0x400 drops out
+            }
+            // column borders                                              xsbl2.v:869-872
+            if (x0 == 0) o[0] = (o[0] & 0xFFFFFF00u) | border;
+            if (x0 + 16 >= W) {
+                const int k = W - 1 - x0;                                  // 0..15
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q == (k >> 2)) o[q] = (o[q] & ~(0xFFu << (8 * (k & 3)))) | (border << (8 * (k & 3)));
+            }
+            o4 = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        o[q] = prmt(r2[0], r2[1], 0x6420);                        // low bytes: 1024 = 0x400 drops out
+        *reinterpret_cast<uint4 *>(dst + (size_t)i * dp) = o4;
     }
-    // column borders                                              xsbl2.v:869-872
-    if (x0 == 0) o[0] = (o[0] & 0xFFFFFF00u) | border;
-    if (x0 + 16 >= W) {
-        const int k = W - 1 - x0;                                  // 0..15
-        o[k >> 2] = (o[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (border << (8 * (k & 3)));
-    }
-    *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 int launch_xsobel(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, size_t src_frame,
                   Img8 dstL, Img8 dstR, int W, int H, int n, int profile, int cap, cudaStream_t s)
 {
     const int tx = 256;
-    dim3 grid((align_up(W, 16) / 16 * H + tx - 1) / tx, 2 * n);
+    dim3 grid((align_up(W, 16) / 16 * ((H + XS_R - 1) / XS_R) + tx - 1) / tx, 2 * n);
     if (profile == U96_PROFILE_RTL)
         k_xsobel<U96_PROFILE_RTL><<<grid, tx, 0, s>>>(srcL, srcR, src_pitch, src_frame, dstL.p, dstR.p, dstL.pitch, dstL.frame, W, H, cap);
     else
