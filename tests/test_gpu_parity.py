@@ -364,3 +364,49 @@ def test_stereobm_facade_maincpp_configuration(u, golden, cv_golden):
     bm.setTextureThreshold(10); bm.setUniquenessRatio(10)
     bm.setSpeckleWindowSize(50); bm.setSpeckleRange(32); bm.setDisp12MaxDiff(1)
     assert np.array_equal(bm.compute(golden["rect_l"], golden["rect_r"]), cv_golden["maincpp_postfilter"])
+
+
+@pytest.mark.parametrize("D,B,T,U,cap", [(64, 21, 10, 10, 31), (64, 9, 0, 0, 31), (64, 5, 25, 30, 63), (128, 15, 10, 15, 31),
+                                         (128, 31, 0, 5, 20), (256, 21, 10, 10, 31), (256, 7, 3, 40, 31)])
+def test_opencv_profile_fast_path_slices(u, fe640, golden, oracle, D, B, T, U, cap):
+    """cv::StereoBM profile on the cluster-sliced kernel (numDisparities = 64 x cluster size): winner, exact uniqueness
+    and sub-pixel neighbours across slice boundaries, texture lane."""
+    for src in ("golden", "synth"):
+        L, R = (golden["rect_l"], golden["rect_r"]) if src == "golden" else u.synth_pair(5, D, 640, 480, min(D, 200))
+        fe640.set_bm_params(width=640, height=480, profile=u.PROFILE_OPENCV, num_disparities=D, block_size=B, texture_threshold=T,
+                            uniqueness_ratio=U, prefilter_cap=cap, min_disparity=0, disp12_max_diff=-1, speckle_window_size=0)
+        fe640.submit_rect(0, L, R)
+        d = fe640.receive_disp(fe640.wait())[0]
+        want = oracle.bm_cv(oracle.xsobel_cv(L, cap), oracle.xsobel_cv(R, cap), wsz=B, ndisp=D, prefilter_cap=cap, texture_threshold=T, uniqueness_ratio=U)
+        assert np.array_equal(d, want), (src, int((d != want).sum()))
+
+
+@pytest.mark.parametrize("D,B,thr", [(128, 21, 921), (128, 9, 700), (256, 21, 921), (256, 15, 500)])
+def test_bm_rtl_uniqueness_across_slices(u, fe640, golden, oracle, D, B, thr):
+    """RTL profile with the uniqueness filter on: the approximate min2 travels through every dphase merge
+    (bm_calc_upd.v), i.e. across the cluster's slice records."""
+    ext = int(D > 128)
+    d = run_xsbl(fe640, 0, golden["xsbl_l"], golden["xsbl_r"],
+                 **dict(RTL, num_disparities=D, block_size=B, rtl_extended=ext, uni_enable=1, uni_thr=thr))[0]
+    want = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=B, ndisp=D, rtl_extended=ext, uni_enb=1, uni_thr=thr)
+    assert np.array_equal(d, want), int((d != want).sum())
+
+
+def test_fast_and_generic_bm_kernels_agree(u, monkeypatch):
+    """The generic kernel (U96_BM_GENERIC=1) and the fast path produce identical maps on a ragged width."""
+    W, H, D = 1000, 131, 128
+    L, R = u.synth_batch(9, 0, 3, W, H, D)
+    outs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("U96_BM_GENERIC", "1")
+        with u.StereoFrontEnd(0, W, H, 3) as fe:
+            res = []
+            for prof in (u.PROFILE_RTL, u.PROFILE_OPENCV):
+                fe.set_bm_params(width=W, height=H, profile=prof, num_disparities=D, block_size=11, x_store_offset=1,
+                                 texture_threshold=10, uniqueness_ratio=10, prefilter_cap=31, uni_enable=1, uni_thr=900)
+                fe.submit_rect(0, L, R)
+                res.append(fe.receive_disp(fe.wait()))
+            outs.append(res)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)

@@ -6,9 +6,10 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libu96stereo.so")
-SOURCES = ["u96_stereo.cu", "rect.cu", "xsobel.cu", "bm.cu", "bm_fast.cu", "reproject.cu", "postfilter.cu", "microbench.cu"]
+SOURCES = ["u96_stereo.cu", "rect.cu", "xsobel.cu", "bm.cu", "bm_fast_cs1.cu", "bm_fast_cs2.cu", "bm_fast_cs4.cu", "reproject.cu", "postfilter.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+OBJDIR = os.path.join(PKG, "lib", "obj")
 
 
 def needs_build():
@@ -24,8 +25,21 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(PKG, "..", "include", "u96_stereo.h")]
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, src[:-3] + ".o")
+        path = os.path.join(CSRC, src)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(path), hdr_t):
+            subprocess.check_call([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj])
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor      # translation units compile side by side (the BM templates dominate)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
     return LIB
 
 

@@ -404,6 +404,23 @@ static bool bm_fill_args(const BmConfig &c, BmArgs &a)
     return true;
 }
 
+// The fast path (bm_fast.cuh) covers numDisparities 64/128/256 (one 64-disparity slice per CTA of a cluster) for both profiles.
+bool bm_fast_supported(const BmConfig &c)
+{
+    if (c.D != 64 && c.D != 128 && c.D != 256) return false;
+    if (c.wsz < 3 || c.wsz > 31) return false;
+    if (c.profile == U96_PROFILE_OPENCV) return c.wsz >= 5 && c.cap >= 1 && c.cap <= 63;
+    return c.profile == U96_PROFILE_RTL;
+}
+
+int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
+                   const BmConfig &c, int n, cudaStream_t s)
+{
+    if (c.D == 64) return launch_bm_fast_cs1(xl, xr, pitch, frame, disp, c, n, s);
+    if (c.D == 128) return launch_bm_fast_cs2(xl, xr, pitch, frame, disp, c, n, s);
+    return launch_bm_fast_cs4(xl, xr, pitch, frame, disp, c, n, s);
+}
+
 int bm_smem_bytes(const BmConfig &c)
 {
     BmArgs a;
@@ -431,8 +448,10 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
         const int y_lo = ok ? b.y_lo : c.H, y_hi = ok ? b.y_hi : c.H, x_lo = ok ? b.ctr_lo + off : c.W, x_hi = ok ? b.ctr_hi + off : c.W;
         k_fill_border<<<dim3((c.H + FB_ROWS - 1) / FB_ROWS, n), 256, 0, s>>>(disp.p, disp.pitch, disp.frame, c.W, c.H, y_lo, y_hi, x_lo, x_hi, inv);
     }
-    if (bm_fast_supported(c) && !getenv("U96_BM_GENERIC"))
-        return 1 + launch_bm_fast(xl, xr, pitch, frame, disp, c, n, s);
+    if (bm_fast_supported(c) && !getenv("U96_BM_GENERIC")) {
+        const int k = launch_bm_fast(xl, xr, pitch, frame, disp, c, n, s);
+        if (k) return 1 + k;
+    }
     BmArgs a;
     if (!bm_fill_args(c, a)) return 1;
     a.xl = xl; a.xr = xr; a.disp = disp.p; a.cost = c.cost; a.pitch = pitch; a.frame = frame;

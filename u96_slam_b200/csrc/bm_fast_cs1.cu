@@ -1,0 +1,12 @@
+// bm_fast_cs1.cu -- instantiations of the fast BM kernel for numDisparities = 64 (cluster of 1 CTA); see bm_fast.cuh.
+#include "bm_fast.cuh"
+
+namespace u96 {
+
+int launch_bm_fast_cs1(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
+                        const BmConfig &c, int n, cudaStream_t s)
+{
+    return launch_bm_fast_cs<1>(xl, xr, pitch, frame, disp, c, n, s);
+}
+
+}  // namespace u96

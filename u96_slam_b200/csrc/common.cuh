@@ -47,6 +47,9 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
 bool bm_fast_supported(const BmConfig &c);
 int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
                    const BmConfig &c, int n, cudaStream_t s);
+int launch_bm_fast_cs1(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
+int launch_bm_fast_cs2(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
+int launch_bm_fast_cs4(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
 
 // cv::StereoBM post filters (OPENCV profile): validateDisparity then filterSpeckles; scratch = 2 int32 per pixel of the batch
 int launch_postfilter(Img16 disp, const int16_t *cost, int W, int H, int n, int ndisp, int disp12_max_diff,
