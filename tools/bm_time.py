@@ -15,9 +15,9 @@ o = Oracle()
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 cfgs = [(640, 480, 64, 21, 0), (640, 480, 64, 15, 0), (640, 480, 64, 9, 0), (640, 480, 64, 21, 1)]
 if len(sys.argv) > 2 and sys.argv[2] == "all":
-    cfgs += [(1242, 375, 128, 15, 0), (1920, 1080, 256, 21, 0)]
+    cfgs += [(1242, 375, 128, 15, 0), (1242, 375, 128, 15, 1), (1242, 375, 128, 21, 0), (1920, 1080, 256, 21, 0), (1920, 1080, 256, 21, 1)]
 for (W, H, D, B, prof) in cfgs:
-    n = nb if W == 640 else max(8, nb * 640 * 480 * 64 // (W * H * D))
+    n = nb if W == 640 else (nb // 2 if W == 1242 else max(8, nb * 32 // 296))
     L, R = u.synth_batch(1, 0, 4, W, H, D)
     reps = (n + 3) // 4
     hL = np.concatenate([L] * reps)[:n]; hR = np.concatenate([R] * reps)[:n]
