@@ -275,7 +275,7 @@ def main():
         for _ in range(min(k, 2)):
             fe2.wait()
 
-    e2e_steps = max(4, args.steps // 2)
+    e2e_steps = max(4, args.steps)
     e2e_loop(3)
     torch.cuda.synchronize()
     if world > 1:
@@ -289,6 +289,24 @@ def main():
     e2e_fps = nb * e2e_steps * world / float(t_e2e.item())
     checksum = int(pD[0][0].to(torch.int64).sum().item())
     fe2.close()
+    # PCIe ceiling of that loop: the same pinned buffers copied both ways at once, no kernels (explains e2e vs value)
+    pcie = None
+    if rank == 0:
+        dI = torch.empty_like(pL, device="cuda"); dO = torch.empty_like(pD[0], device="cuda")
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        best = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(2):
+                with torch.cuda.stream(s_in):
+                    dI.copy_(pL, non_blocking=True); dI.copy_(pR, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    pD[1].copy_(dO, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, 2 * 2 * pL.numel() / (time.perf_counter() - t0) / 1e9)
+        pcie = {"bidir_gbs_per_direction": best, "ceiling_frames_per_s": best * 1e9 / (2.0 * W * H),
+                "note": "pinned H2D of the step's inputs and D2H of its disparity maps issued together, no kernels"}
+        del dI, dO
 
     if rank == 0:
         # ---- roofline of the dominant kernel (k_bm): integer pipe, measured issue rate as the peak ----
@@ -337,7 +355,8 @@ def main():
                                  f"inputs {in_bytes / 1e6:.0f} MB per step (<L2; intermediates {7 * in_bytes / 2e6:.0f} MB)"},
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(2 * W * H * nb),
                         "d2h_bytes_per_step": int(2 * W * H * nb), "steps": e2e_steps, "checksum": checksum,
-                        "timing": "wall clock around u96_submit_raw_async/u96_wait over two banks, synchronize on both sides"},
+                        "timing": "wall clock around u96_submit_raw_async/u96_wait over two banks, synchronize on both sides",
+                        "pcie": pcie},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -24,6 +24,7 @@
 // Disparity slots: s in [0,D) <-> d = s.  RTL adds the two guard lanes of the first/last dphase
 // (d = -1 -> slot D, d = D -> slot D+1; bm_calc_sad.v:353-418 lanes 0 and 33) which only feed the
 // sub-pixel stage.  OPENCV adds the texture lane (|L - cap| -> slot D).  Slots are padded to DP = D+8.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -419,6 +420,21 @@ int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame
     if (c.D == 64) return launch_bm_fast_cs1(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 128) return launch_bm_fast_cs2(xl, xr, pitch, frame, disp, c, n, s);
     return launch_bm_fast_cs4(xl, xr, pitch, frame, disp, c, n, s);
+}
+
+// Frames whose BM grid fills the device exactly once (2 CTAs per SM on the fast path): the chunk pipeline of the
+// C ABI cuts host batches at multiples of this so that no chunk runs the SMs half empty.
+int bm_wave_frames(const BmConfig &c)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int h = c.wsz >> 1;
+    const int ncen = (c.profile == U96_PROFILE_RTL) ? (c.W - 2 - h) - (c.D + h) + 1 : (c.W - 1 - h) - (c.D - 1 + h) + 1;
+    if (ncen <= 0) return 1;
+    const int tx5 = 160 - 2 * h, tx4 = 128 - 2 * h;
+    const int tiles = std::min((ncen + tx5 - 1) / tx5, (ncen + tx4 - 1) / tx4) * std::max(1, c.D / 64);
+    return std::max(1, (2 * sms + tiles - 1) / tiles);
 }
 
 int bm_smem_bytes(const BmConfig &c)

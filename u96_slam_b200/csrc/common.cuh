@@ -41,6 +41,7 @@ struct BmConfig {
     int16_t *cost = nullptr;                                           // OPENCV: winning SAD per valid pixel (same pitch as disp) or null
 };
 int  bm_smem_bytes(const BmConfig &c);
+int  bm_wave_frames(const BmConfig &c);
 int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
               const BmConfig &c, int n, cudaStream_t s);
 

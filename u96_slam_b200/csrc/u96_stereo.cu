@@ -26,6 +26,14 @@ static thread_local std::string g_cuda_err;
 
 namespace {
 
+// 2-D copy that degenerates to one contiguous transfer when both pitches equal the row width (640-wide images in
+// 640-byte rows): the DMA engines move one large block far faster than hundreds of thousands of row descriptors.
+cudaError_t copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
+}
+
 enum { FROM_RAW = 0, FROM_RECT = 1, FROM_XSBL = 2 };
 
 struct Bank {
@@ -348,28 +356,30 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     if (!pipelined) {
         if (!zero_copy)
             for (int i = 0; i < 2; i++)
-                CK(cudaMemcpy2DAsync(dstbuf[i], pitch, src[i], stride, W, (size_t)H * n,
+                CK(copy2d(dstbuf[i], pitch, src[i], stride, W, (size_t)H * n,
                                      device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
         if (h->profiling) CK(cudaEventRecord(k.ev[1], s));
         const int rc = run_range(h, k, from, 0, n, s, h->profiling);
         if (rc != U96_OK) return rc;
         if (disp_out)
-            CK(cudaMemcpy2DAsync(disp_out, (size_t)W * 2, k.disp, (size_t)pitch * 2, (size_t)W * 2, (size_t)H * n, cudaMemcpyDeviceToHost, s));
+            CK(copy2d(disp_out, (size_t)W * 2, k.disp, (size_t)pitch * 2, (size_t)W * 2, (size_t)H * n, cudaMemcpyDeviceToHost, s));
     } else {
-        const int nchunks = std::min(8, n / 32);
-        const int csz = (n + nchunks - 1) / nchunks;
+        // chunks of whole BM waves (a chunk that fills half the SMs would make the kernels, not PCIe, the bottleneck)
+        const int wave = bm_wave_frames(bm_config(h->bm));
+        int csz = std::max(wave, (32 + wave - 1) / wave * wave);
+        if (csz > n) csz = n;
         CK(cudaEventRecord(k.done, s));                       // the sub-streams start behind whatever the bank stream holds
         for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(k.sub[i], k.done, 0));
         for (int c = 0, f0 = 0; f0 < n; c++, f0 += csz) {
             const int nf = std::min(csz, n - f0);
             cudaStream_t cs = k.sub[c % 3];
             for (int i = 0; i < 2; i++)
-                CK(cudaMemcpy2DAsync(dstbuf[i] + (size_t)f0 * frame, pitch, src[i] + (size_t)f0 * stride * H, stride, W, (size_t)H * nf,
+                CK(copy2d(dstbuf[i] + (size_t)f0 * frame, pitch, src[i] + (size_t)f0 * stride * H, stride, W, (size_t)H * nf,
                                      cudaMemcpyHostToDevice, cs));
             const int rc = run_range(h, k, from, f0, nf, cs, false);
             if (rc != U96_OK) return rc;
             if (disp_out)
-                CK(cudaMemcpy2DAsync(disp_out + (size_t)f0 * W * H, (size_t)W * 2, k.disp + (size_t)f0 * frame, (size_t)pitch * 2,
+                CK(copy2d(disp_out + (size_t)f0 * W * H, (size_t)W * 2, k.disp + (size_t)f0 * frame, (size_t)pitch * 2,
                                      (size_t)W * 2, (size_t)H * nf, cudaMemcpyDeviceToHost, cs));
         }
         for (int i = 0; i < 3; i++) {                         // join: the bank stream (and `done`) follows all chunks
@@ -396,7 +406,7 @@ static int receive_u8(u96_handle *h, int bank, const uint8_t *const cur[2], int 
     (void)frame;
     uint8_t *dst[2] = {L, R};
     for (int i = 0; i < 2; i++)
-        CK(cudaMemcpy2DAsync(dst[i], W, cur[i], pitch, W, (size_t)H * k.n, cudaMemcpyDeviceToHost, s));
+        CK(copy2d(dst[i], W, cur[i], pitch, W, (size_t)H * k.n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return U96_OK;
 }
@@ -455,7 +465,7 @@ int u96_receive_disp(u96_handle *h, int bank, int16_t *disp)
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
     const int W = h->bm.width, H = h->bm.height;
-    CK(cudaMemcpy2DAsync(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
+    CK(copy2d(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
                          cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return U96_OK;
@@ -469,7 +479,7 @@ int u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp)
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
     const int W = h->bm.width, H = h->bm.height;
-    CK(cudaMemcpy2DAsync(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
+    CK(copy2d(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
                          cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(k.done, s));                          // wait() now covers the copy as well
     return U96_OK;
