@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define U96_ABI_VERSION 2
+#define U96_ABI_VERSION 3
 
 enum {
     U96_OK = 0,
@@ -131,6 +131,13 @@ int  u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp);
  * flags bit0: apply StereoCameraModel localTransform (StereoCameraModel.cpp:9-14). */
 int  u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_r[12],
                    int decim, int flags, float *xyz);
+
+/* Xusb_ReceiveData (StereoBM/src/xusb_main.c:293-376): the UVC payload the R5 firmware streams for a bank -- per pair one
+ * YUYV frame of 2W x H pixels (2 bytes per pixel, chroma byte 0x80): left half = left image / disparity, right half =
+ * right image / zero.  which: U96_UVC_RECT (USB_OUTPUT_STEREO_RECT), U96_UVC_XSBL (USB_OUTPUT_STEREO_XSBL),
+ * U96_UVC_BM (USB_OUTPUT_STEREO_BM: Y = (u8)(s16 disparity >> 4)).  frame = n * H * 2W * 2 bytes (host). */
+enum { U96_UVC_RECT = 1, U96_UVC_XSBL = 2, U96_UVC_BM = 3 };
+int  u96_receive_uvc(u96_handle *h, int bank, int which, uint8_t *frame);
 
 /* device address + row pitch of a bank image (results stay resident for a GPU consumer) */
 int  u96_bank_device_ptr(u96_handle *h, int bank, int which, void **dptr, int *pitch_bytes, size_t *frame_bytes);

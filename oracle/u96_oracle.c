@@ -531,3 +531,24 @@ void orc_reproject(const int16_t *disp, int W, int H, const double *P_l, const d
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * UVC payload: Xusb_ReceiveData, StereoBM/src/xusb_main.c:293-376.  The firmware's loops hard-code 640x480 and the
+ * FPGA's DDR layouts (RECT: planar, XSBL: interleaved {L,R} words read back to front); here the inputs are the
+ * planar images of the C ABI, the OUTPUT layout is the firmware's: dst[(row*2W + col + lr*W)*2] = Y, +1 = 0x80
+ * (:313-327), disparity mode Y = (u8)(s16 >> 4) on the left half and 0x00 on the right (:356-372). */
+void orc_pack_uvc(int mode, const uint8_t *L, const uint8_t *R, const int16_t *disp, int W, int H, uint8_t *frame)
+{
+    for (int row = 0; row < H; row++)
+        for (int col = 0; col < W; col++) {
+            size_t dl = ((size_t)row * 2 * W + col) * 2, dr = ((size_t)row * 2 * W + col + W) * 2;
+            if (mode == 3) {
+                int16_t t = disp[(size_t)row * W + col];
+                t = (int16_t)(t >> 4);
+                frame[dl] = (uint8_t)t; frame[dr] = 0x00;
+            } else {
+                frame[dl] = L[(size_t)row * W + col]; frame[dr] = R[(size_t)row * W + col];
+            }
+            frame[dl + 1] = 0x80; frame[dr + 1] = 0x80;
+        }
+}

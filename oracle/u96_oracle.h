@@ -97,6 +97,10 @@ void orc_filter_speckles(int16_t *img, int W, int H, int new_val, int max_size, 
 void orc_reproject(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
                    int decim, int apply_local, float *xyz);
 
+/* UVC payload of the firmware (StereoBM/src/xusb_main.c:293-376): YUYV frame of 2W x H pixels.
+ * mode 1 = USB_OUTPUT_STEREO_RECT / 2 = USB_OUTPUT_STEREO_XSBL (planar u8 L and R) / 3 = USB_OUTPUT_STEREO_BM (s16 disparity). */
+void orc_pack_uvc(int mode, const uint8_t *L, const uint8_t *R, const int16_t *disp, int W, int H, uint8_t *frame);
+
 #ifdef __cplusplus
 }
 #endif

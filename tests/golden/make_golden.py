@@ -12,6 +12,7 @@ Outputs
                       ref_rect for several parameter sets, post filters off
                       (speckleWindowSize=0, disp12MaxDiff=-1) and, for the
                       main.cpp parameter set, also with them on.
+  dat_sha256.json   : SHA-256 and length of the four reference .dat text files (pins write_dat).
   rect_remap_ref.npz: output of the reference's own rect_remap() (fpga.c:303-366,
                       compiled from where it lies into oracle/_ref) for the
                       shipped parameter set (fpga.c:190-226).
@@ -38,8 +39,21 @@ def read_dat(name):
     return a
 
 
+def dat_digests():
+    """SHA-256 of the reference's .dat text files: pins the byte-exact writer u96_slam_b200.formats.write_dat."""
+    import hashlib
+    import json
+    d = {}
+    for name in ("ref_rect_l", "ref_rect_r", "ref_xsbl_l", "ref_xsbl_r"):
+        with zipfile.ZipFile(os.path.join(REF, "data", name + ".zip")) as z:
+            b = z.read(z.namelist()[0])
+        d[name] = {"sha256": hashlib.sha256(b).hexdigest(), "bytes": len(b)}
+    json.dump(d, open(os.path.join(HERE, "dat_sha256.json"), "w"), indent=1)
+
+
 def main():
     import cv2
+    dat_digests()
 
     rl, rr = read_dat("ref_rect_l"), read_dat("ref_rect_r")
     xl, xr = read_dat("ref_xsbl_l"), read_dat("ref_xsbl_r")

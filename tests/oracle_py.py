@@ -92,6 +92,21 @@ class Oracle:
                                     ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
                                     ctypes.POINTER(ctypes.c_float)]
 
+    def pack_uvc(self, mode, L=None, R=None, disp=None):
+        """UVC payload (xusb_main.c:293-376): mode 1 rect / 2 xsbl (planar u8 L, R), 3 disparity (s16)"""
+        u8p = ctypes.POINTER(ctypes.c_uint8); i16p = ctypes.POINTER(ctypes.c_int16)
+        if mode == 3:
+            disp = np.ascontiguousarray(disp, np.int16); H, W = disp.shape
+            a = (None, None, disp.ctypes.data_as(i16p))
+        else:
+            L = np.ascontiguousarray(L, np.uint8); R = np.ascontiguousarray(R, np.uint8); H, W = L.shape
+            a = (L.ctypes.data_as(u8p), R.ctypes.data_as(u8p), None)
+        out = np.empty((H, 2 * W, 2), np.uint8)
+        self.L.orc_pack_uvc.argtypes = [ctypes.c_int, u8p, u8p, i16p, ctypes.c_int, ctypes.c_int, u8p]
+        self.L.orc_pack_uvc.restype = None
+        self.L.orc_pack_uvc(mode, a[0], a[1], a[2], W, H, out.ctypes.data_as(u8p))
+        return out
+
     def diven(self, DW, VW, QW, MSB_INV, dividend, divisor):
         return int(self.L.orc_diven(DW, VW, QW, MSB_INV, dividend & (2**64 - 1), divisor & (2**64 - 1)))
 

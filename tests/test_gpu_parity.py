@@ -410,3 +410,24 @@ def test_fast_and_generic_bm_kernels_agree(u, monkeypatch):
             outs.append(res)
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def test_uvc_payload(u, fe640, golden, oracle):
+    """u96_receive_uvc == the firmware's UVC frame (xusb_main.c:293-376) for the RECT, XSBL and BM streams."""
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    L2 = np.stack([golden["rect_l"], golden["rect_r"]]); R2 = np.stack([golden["rect_r"], golden["rect_l"]])
+    fe640.submit_rect(0, L2, R2)
+    b = fe640.wait()
+    sl, sr = fe640.receive_xsbl(b); d = fe640.receive_disp(b)
+    for i in range(2):
+        assert np.array_equal(fe640.receive_uvc(b, u.UVC_RECT)[i], oracle.pack_uvc(1, L2[i], R2[i]))
+        assert np.array_equal(fe640.receive_uvc(b, u.UVC_XSBL)[i], oracle.pack_uvc(2, sl[i], sr[i]))
+        assert np.array_equal(fe640.receive_uvc(b, u.UVC_BM)[i], oracle.pack_uvc(3, disp=d[i]))
+    # ragged width (W not a multiple of 8)
+    W, H = 650, 37
+    L, R = u.synth_batch(4, 0, 1, W, H, 64)
+    with u.StereoFrontEnd(0, W, H, 1) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=9, num_disparities=64, x_store_offset=1)
+        fe.submit_rect(0, L, R); b = fe.wait()
+        assert np.array_equal(fe.receive_uvc(b, u.UVC_BM)[0], oracle.pack_uvc(3, disp=fe.receive_disp(b)[0]))
+        assert np.array_equal(fe.receive_uvc(b, u.UVC_RECT)[0], oracle.pack_uvc(1, L[0], R[0]))

@@ -184,3 +184,57 @@ def test_postfilters_match_opencv_public_functions(oracle, golden, cv_golden):
         a = disp.copy(); oracle.L.orc_filter_speckles(a.ctypes.data_as(i16p), W, H, -16, size, diff)
         b = disp.copy(); cv2.filterSpeckles(b, -16, size, diff)
         assert np.array_equal(a, b) and (a != disp).sum() > 100
+
+
+def test_dat_writer_reproduces_reference_files_byte_for_byte(golden):
+    """formats.write_dat(golden image) == the reference's data/ref_*.dat text (SHA-256 recorded by make_golden.py);
+    read_dat is its inverse."""
+    import hashlib
+    import json
+    import u96_slam_b200.formats as fm
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dat_sha256.json")))
+    for key, name in (("rect_l", "ref_rect_l"), ("rect_r", "ref_rect_r"), ("xsbl_l", "ref_xsbl_l"), ("xsbl_r", "ref_xsbl_r")):
+        b = fm.write_dat(golden[key])
+        assert len(b) == want[name]["bytes"] and hashlib.sha256(b).hexdigest() == want[name]["sha256"], name
+        assert np.array_equal(fm.read_dat(b, width=640), golden[key])
+
+
+def test_uvc_payload_oracle_follows_firmware_loops(oracle, golden):
+    """orc_pack_uvc against a literal numpy transcription of Xusb_ReceiveData's index arithmetic (xusb_main.c:313-372)."""
+    L, R = golden["rect_l"], golden["rect_r"]
+    f = oracle.pack_uvc(1, L, R)
+    flat = f.reshape(-1)
+    rows, cols = np.mgrid[0:480, 0:640]
+    for lr, img in ((0, L), (1, R)):
+        dst = (rows * 1280 + cols + lr * 640) * 2
+        assert np.array_equal(flat[dst], img) and (flat[dst + 1] == 0x80).all()
+    d = (np.arange(480 * 640, dtype=np.int32).reshape(480, 640) * 37 % 2200 - 100).astype(np.int16)
+    d[::7, ::5] = -1
+    f = oracle.pack_uvc(3, disp=d).reshape(-1)
+    dl, dr = (rows * 1280 + cols) * 2, (rows * 1280 + cols + 640) * 2
+    assert np.array_equal(f[dl], (d >> 4).astype(np.uint8)) and (f[dr] == 0).all() and (f[dl + 1] == 0x80).all() and (f[dr + 1] == 0x80).all()
+
+
+def test_rect_registers_from_calibration(oracle):
+    """rect_params_from_calibration: identity calibration reproduces the near-identity register set, and for a rotated rig
+    the fixed-point map of rect_remap (fpga.c:303-366) follows K R^T K'^-1 to within the u10.5 output resolution."""
+    import u96_slam_b200 as u
+    W, H, f = 640, 480, 700.0
+    ident = u.rect_params_from_calibration([(f, f, W / 2, H / 2)] * 2, [np.eye(3)] * 2, (f, f, W / 2, H / 2))
+    assert ident == u.identity_rect_params(W, H, f)
+
+    def rot(ax, ay, az):
+        cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return Rz @ Ry @ Rx
+    K = [(690.0, 705.0, 318.0, 236.0), (702.0, 699.0, 318.0, 236.0)]
+    Rr = [rot(0.01, -0.02, 0.015), rot(-0.008, 0.012, -0.02)]
+    Kn = (650.0, 650.0, 322.0, 241.0)
+    p = u.rect_params_from_calibration(K, Rr, Kn)
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    for cam in range(2):
+        mx, my = oracle.rect_remap(p, cam, W, H)
+        v = np.stack([(xs - Kn[2]) / Kn[0], (ys - Kn[3]) / Kn[1], np.ones_like(xs)], -1) @ Rr[cam]      # R^T applied to each ray
+        wx = v[..., 0] / v[..., 2] * K[cam][0] + round(K[0][2]); wy = v[..., 1] / v[..., 2] * K[cam][1] + round(K[0][3])
+        assert np.abs(mx / 32.0 - wx).max() < 0.06 and np.abs(my / 32.0 - wy).max() < 0.06

@@ -59,6 +59,10 @@ int launch_postfilter(Img16 disp, const int16_t *cost, int W, int H, int n, int 
 int launch_reproject(const int16_t *disp, int dpitch, size_t dframe, int W, int H, int n,
                      const double *P_l, const double *P_r, int decim, int flags, float *xyz, cudaStream_t s);
 
+// UVC payload (xusb_main.c:293-376): YUYV frame of 2W x H; disp != null selects the disparity mode
+int launch_pack_uvc(const uint8_t *srcL, const uint8_t *srcR, int sp, size_t sf, const int16_t *disp, int dp, size_t df,
+                    uint8_t *out, int W, int H, int n, cudaStream_t s);
+
 int run_microbench(int which, double *gops);
 
 }  // namespace u96

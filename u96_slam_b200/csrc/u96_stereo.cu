@@ -71,6 +71,8 @@ struct u96_handle {
     int64_t launches = 0;
     float *xyz = nullptr;
     size_t xyz_cap = 0;
+    uint8_t *uvc = nullptr;
+    size_t uvc_cap = 0;
 };
 
 static int validate_bm(const u96_handle *h, const u96_bm_params &p)
@@ -192,6 +194,7 @@ void u96_destroy(u96_handle *h)
     cudaFree(h->map);
     rect_plan_free(h->plan);
     cudaFree(h->xyz);
+    cudaFree(h->uvc);
     delete h;
 }
 
@@ -503,6 +506,34 @@ int u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_
     h->launches += launch_reproject(k.disp, h->pitch, (size_t)h->pitch * H, W, H, k.n, P_l, P_r, decim, flags, h->xyz, s);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(xyz, h->xyz, count * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return U96_OK;
+}
+
+int u96_receive_uvc(u96_handle *h, int bank, int which, uint8_t *frame)
+{
+    if (!h || bank < 0 || bank > 1 || !frame) return U96_ERR_INVALID;
+    if (which != U96_UVC_RECT && which != U96_UVC_XSBL && which != U96_UVC_BM) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!k.filled) return U96_ERR_STATE;
+    if ((which == U96_UVC_RECT && k.from > FROM_RECT)) return U96_ERR_STATE;      // the bank holds no rectified images
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    const int W = h->bm.width, H = h->bm.height;
+    const size_t bytes = (size_t)k.n * H * W * 4;
+    if (bytes > h->uvc_cap) {
+        cudaFree(h->uvc); h->uvc = nullptr; h->uvc_cap = 0;
+        if (cudaMalloc(&h->uvc, bytes) != cudaSuccess) return U96_ERR_NOMEM;
+        h->uvc_cap = bytes;
+    }
+    if (which == U96_UVC_BM)
+        h->launches += launch_pack_uvc(nullptr, nullptr, 0, 0, k.disp, h->pitch, (size_t)h->pitch * H, h->uvc, W, H, k.n, s);
+    else if (which == U96_UVC_RECT)
+        h->launches += launch_pack_uvc(k.cur_rect[0], k.cur_rect[1], k.rect_pitch, k.rect_frame, nullptr, 0, 0, h->uvc, W, H, k.n, s);
+    else
+        h->launches += launch_pack_uvc(k.cur_xsbl[0], k.cur_xsbl[1], k.xsbl_pitch, k.xsbl_frame, nullptr, 0, 0, h->uvc, W, H, k.n, s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(frame, h->uvc, bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return U96_OK;
 }

@@ -17,6 +17,7 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 PROFILE_RTL, PROFILE_OPENCV = 0, 1
+UVC_RECT, UVC_XSBL, UVC_BM = 1, 2, 3
 BUF_RAW_L, BUF_RAW_R, BUF_RECT_L, BUF_RECT_R, BUF_XSBL_L, BUF_XSBL_R, BUF_DISP = range(7)
 
 # shipped rectification parameter set (StereoBM/src/fpga.c:190-226)
@@ -92,6 +93,7 @@ def load_library():
     L.u96_receive_rect.argtypes = [vp, i32, u8p, u8p]
     L.u96_receive_xsbl.argtypes = [vp, i32, u8p, u8p]
     L.u96_receive_disp.argtypes = [vp, i32, vp]
+    L.u96_receive_uvc.argtypes = [vp, i32, i32, vp]
     L.u96_enqueue_receive_disp.argtypes = [vp, i32, vp]
     L.u96_reproject.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), i32, i32, vp]
     L.u96_bank_device_ptr.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_size_t)]
@@ -235,6 +237,13 @@ class StereoFrontEnd:
         d = out if out is not None else np.empty((n, self.H, self.W), np.int16)
         _check(self.L, self.L.u96_receive_disp(self.h, bank, d.ctypes.data), "u96_receive_disp")
         return d
+
+    def receive_uvc(self, bank, which):
+        """UVC payload of the firmware (xusb_main.c:293-376): (n, H, 2W, 2) u8 YUYV; which = UVC_RECT / UVC_XSBL / UVC_BM"""
+        n = self._n[bank]
+        f = np.empty((n, self.H, 2 * self.W, 2), np.uint8)
+        _check(self.L, self.L.u96_receive_uvc(self.h, bank, which, f.ctypes.data), "u96_receive_uvc")
+        return f
 
     def receive_disp_ptr(self, bank, host_ptr):
         _check(self.L, self.L.u96_receive_disp(self.h, bank, ctypes.c_void_p(host_ptr)), "u96_receive_disp")
