@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define U96_ABI_VERSION 3
+#define U96_ABI_VERSION 4
 
 enum {
     U96_OK = 0,
@@ -43,7 +43,7 @@ enum { U96_PROFILE_RTL = 0, U96_PROFILE_OPENCV = 1 };
 
 /* which image of a bank (u96_bank_device_ptr) */
 enum { U96_BUF_RAW_L = 0, U96_BUF_RAW_R, U96_BUF_RECT_L, U96_BUF_RECT_R,
-       U96_BUF_XSBL_L, U96_BUF_XSBL_R, U96_BUF_DISP, U96_BUF_COUNT };
+       U96_BUF_XSBL_L, U96_BUF_XSBL_R, U96_BUF_DISP, U96_BUF_EIG, U96_BUF_COUNT };
 
 typedef struct u96_handle u96_handle;
 
@@ -92,6 +92,10 @@ int  u96_set_bm_registers(u96_handle *h, uint32_t image_size, uint32_t bm_settin
 int  u96_get_bm_params(u96_handle *h, u96_bm_params *p);
 /* set_rect_param() (fpga.c:267-301); also rebuilds the on-device map (rect_remap, fpga.c:303-366) */
 int  u96_set_rect_params(u96_handle *h, const u96_rect_params *p);
+/* fpga->gftt.Control = FPGA_GFTT_CTRL_ENABLE (StereoBM/src/fpga.c:162-172; register file dvp/rtl/gftt.v:117-160): when
+ * enabled every submit_raw / submit_rect also produces the min-eigenvalue map of the rectified LEFT image
+ * (gftt.Address_In = BUF_RECT).  Off by default, like the firmware without RETURN_DATA_GFTT. */
+int  u96_set_gftt(u96_handle *h, int enable);
 /* run kernels of this handle on a caller-owned cudaStream_t (NULL = internal per-bank streams) */
 int  u96_set_stream(u96_handle *h, void *cuda_stream);
 
@@ -131,6 +135,11 @@ int  u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp);
  * flags bit0: apply StereoCameraModel localTransform (StereoCameraModel.cpp:9-14). */
 int  u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_r[12],
                    int decim, int flags, float *xyz);
+
+/* Fpga::receiveEigen (FPGA.cpp:281-296): CV_16UC1 min-eigenvalue map (n*H*W u16, rows 0,1,H-2,H-1 zero like the
+ * firmware-cleared GFTT bank) and the per-frame maximum the FPGA latches in gftt.Max (gftt_obuf.v:90-118); max_eig
+ * receives n values (may be NULL).  Needs u96_set_gftt(h, 1) before the submit and a bank filled from raw or rect. */
+int  u96_receive_eigen(u96_handle *h, int bank, uint16_t *eig, uint16_t *max_eig);
 
 /* Xusb_ReceiveData (StereoBM/src/xusb_main.c:293-376): the UVC payload the R5 firmware streams for a bank -- per pair one
  * YUYV frame of 2W x H pixels (2 bytes per pixel, chroma byte 0x80): left half = left image / disparity, right half =

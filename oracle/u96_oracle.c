@@ -552,3 +552,74 @@ void orc_pack_uvc(int mode, const uint8_t *L, const uint8_t *R, const int16_t *d
             frame[dl + 1] = 0x80; frame[dr + 1] = 0x80;
         }
 }
+
+/* ---- GFTT min-eigenvalue map: dvp/rtl/gftt*.v ------------------------------------------------
+ * Stage by stage, with the RTL's bit widths:
+ *  gftt_ibuf.v:385-415   three-line window; the Sobel stream covers image rows 1..H-2 (row2==2 gate, :385-398)
+ *  gftt_sbl.v:118-205    dx = x-Sobel, dy = y-Sobel (s11.0); 0 at columns 0 and W-1 (first/last sample, :151, :198)
+ *  gftt_eig.v:104-124    |dx|,|dy| (abs11) ; dx2=|dx|^2>>6, dy2=|dy|^2>>6, dxdy=|dx||dy|>>6  (the SIGN of dx*dy is dropped)
+ *  gftt_box.v:185,232-262  3x3 box: horizontal 3-sum forced to 0 at columns 0 and W-1, three line sums, limit to 0xFFFF;
+ *                        box rows are image rows 2..H-3 (line_ready, :131-140)
+ *  gftt_eig.v:196-287    apc=a+c (17 bit) ; amc=|a-c| ; amc2=(amc^2)>>10 (22 bit) ; b2=(b^2)>>8 (24 bit) ;
+ *                        s=min(amc2+b2, 0x3FFFFF) ; root = CORDIC sqrt IP, UnsignedFraction 32 -> 17 bit, Truncate
+ *                        (ip/gftt_sqrt/gftt_sqrt.xci) on {0, s, 9'b0}:  in = s*2^9/2^31, out = sqrt(in)*2^16
+ *                        = floor(sqrt(s * 2^10))  [IP modelled as an exact truncating square root: PARITY UNPINNED,
+ *                        the encrypted IP model cannot be run here and the reference ships no eigen dump]
+ *  gftt_eig.v:293-310    eig = apc - root[15:0] (18 bit signed): <0 -> 0 ; bit 16 -> 0xFFFF ; else eig[15:0]
+ *  gftt_obuf.v:90-118, 262-275  per-frame maximum of the stream ; rows 2..H-3 written at a two-line offset, the bank is
+ *                        zeroed by the firmware (fpga.c:107-108) so rows 0,1,H-2,H-1 read 0.
+ * eig: W*H u16 row-major (what Fpga::receiveEigen returns, FPGA.cpp:281-296); *max_out = reg gftt.Max of the bank. */
+static uint32_t orc_isqrt32(uint32_t x)
+{
+    uint32_t r = 0;
+    for (int b = 15; b >= 0; b--) {
+        const uint32_t t = r | (1u << b);
+        if ((uint64_t)t * t <= x) r = t;
+    }
+    return r;
+}
+
+void orc_gftt_eig(const uint8_t *src, int W, int H, int src_stride, uint16_t *eig, uint16_t *max_out)
+{
+    const size_t np = (size_t)W * H;
+    uint16_t *v[3];                       /* dx2, dy2, dxdy (u16) on the Sobel rows */
+    uint32_t *hs[3];                      /* horizontal 3-sums (18 bit)             */
+    for (int k = 0; k < 3; k++) { v[k] = (uint16_t *)calloc(np, sizeof(uint16_t)); hs[k] = (uint32_t *)calloc(np, sizeof(uint32_t)); }
+    memset(eig, 0, np * sizeof(uint16_t));
+    for (int y = 1; y <= H - 2; y++)
+        for (int x = 1; x <= W - 2; x++) {
+            const uint8_t *p0 = src + (size_t)(y - 1) * src_stride, *p1 = src + (size_t)y * src_stride, *p2 = src + (size_t)(y + 1) * src_stride;
+            const int dx = (p0[x + 1] - p0[x - 1]) + 2 * (p1[x + 1] - p1[x - 1]) + (p2[x + 1] - p2[x - 1]);
+            const int dy = (p2[x - 1] - p0[x - 1]) + 2 * (p2[x] - p0[x]) + (p2[x + 1] - p0[x + 1]);
+            const uint32_t ax = (uint32_t)(dx < 0 ? -dx : dx) & 0x7FF, ay = (uint32_t)(dy < 0 ? -dy : dy) & 0x7FF;
+            v[0][(size_t)y * W + x] = (uint16_t)((ax * ax) >> 6);
+            v[1][(size_t)y * W + x] = (uint16_t)((ay * ay) >> 6);
+            v[2][(size_t)y * W + x] = (uint16_t)((ax * ay) >> 6);
+        }
+    for (int k = 0; k < 3; k++)
+        for (int y = 1; y <= H - 2; y++)
+            for (int x = 1; x <= W - 2; x++)
+                hs[k][(size_t)y * W + x] = (uint32_t)v[k][(size_t)y * W + x - 1] + v[k][(size_t)y * W + x] + v[k][(size_t)y * W + x + 1];
+    uint16_t mx = 0;
+    for (int y = 2; y <= H - 3; y++)
+        for (int x = 0; x < W; x++) {
+            uint32_t box[3];
+            for (int k = 0; k < 3; k++) {
+                const uint32_t s = hs[k][(size_t)(y - 1) * W + x] + hs[k][(size_t)y * W + x] + hs[k][(size_t)(y + 1) * W + x];
+                box[k] = s > 0xFFFFu ? 0xFFFFu : s;
+            }
+            const uint32_t a = box[0], c = box[1], b = box[2];
+            const uint32_t apc = a + c;
+            const uint32_t amc = a > c ? a - c : c - a;
+            const uint32_t amc2 = (amc * amc) >> 10, b2 = (b * b) >> 8;
+            uint32_t s = amc2 + b2;
+            if (s > 0x3FFFFFu) s = 0x3FFFFFu;
+            const uint32_t root = orc_isqrt32(s << 10) & 0xFFFFu;
+            const int32_t e = (int32_t)apc - (int32_t)root;
+            const uint16_t o = e < 0 ? 0 : (e & 0x10000) ? 0xFFFF : (uint16_t)e;
+            eig[(size_t)y * W + x] = o;
+            if (o > mx) mx = o;
+        }
+    if (max_out) *max_out = mx;
+    for (int k = 0; k < 3; k++) { free(v[k]); free(hs[k]); }
+}

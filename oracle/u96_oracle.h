@@ -101,6 +101,12 @@ void orc_reproject(const int16_t *disp, int W, int H, const double *P_l, const d
  * mode 1 = USB_OUTPUT_STEREO_RECT / 2 = USB_OUTPUT_STEREO_XSBL (planar u8 L and R) / 3 = USB_OUTPUT_STEREO_BM (s16 disparity). */
 void orc_pack_uvc(int mode, const uint8_t *L, const uint8_t *R, const int16_t *disp, int W, int H, uint8_t *frame);
 
+/* ---- GFTT min-eigenvalue map: dvp/rtl/gftt{,_ibuf,_sbl,_eig,_box,_obuf}.v ----------------
+ * src: rectified LEFT image (gftt.Address_In = BUF_RECT, fpga.c:166-167).  eig: W*H u16 (rows 0,1,H-2,H-1 = 0),
+ * *max_out = per-frame maximum (gftt.Max register).  The CORDIC sqrt IP is modelled as an exact truncating
+ * square root: PARITY UNPINNED (no eigen dump in the reference, IP model not runnable here).                */
+void orc_gftt_eig(const uint8_t *src, int W, int H, int src_stride, uint16_t *eig, uint16_t *max_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,16 @@ class Oracle:
         self.L.orc_pack_uvc(mode, a[0], a[1], a[2], W, H, out.ctypes.data_as(u8p))
         return out
 
+    def gftt_eig(self, src):
+        """dvp/rtl/gftt*.v -> (H, W) u16 min-eigenvalue map, per-frame maximum (gftt.Max)"""
+        a, p = _u8(src); H, W = a.shape
+        out = np.empty((H, W), np.uint16); mx = ctypes.c_uint16(0)
+        u16p = ctypes.POINTER(ctypes.c_uint16)
+        self.L.orc_gftt_eig.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, u16p, u16p]
+        self.L.orc_gftt_eig.restype = None
+        self.L.orc_gftt_eig(p, W, H, W, out.ctypes.data_as(u16p), ctypes.byref(mx))
+        return out, int(mx.value)
+
     def diven(self, DW, VW, QW, MSB_INV, dividend, divisor):
         return int(self.L.orc_diven(DW, VW, QW, MSB_INV, dividend & (2**64 - 1), divisor & (2**64 - 1)))
 

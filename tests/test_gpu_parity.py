@@ -431,3 +431,46 @@ def test_uvc_payload(u, fe640, golden, oracle):
         fe.submit_rect(0, L, R); b = fe.wait()
         assert np.array_equal(fe.receive_uvc(b, u.UVC_BM)[0], oracle.pack_uvc(3, disp=fe.receive_disp(b)[0]))
         assert np.array_equal(fe.receive_uvc(b, u.UVC_RECT)[0], oracle.pack_uvc(1, L[0], R[0]))
+
+
+def test_gftt_min_eigenvalue_map(u, fe640, golden, oracle):
+    """u96_set_gftt + u96_receive_eigen == the oracle's reading of dvp/rtl/gftt*.v (map and gftt.Max), on the bundled pair,
+    through the raw path (GFTT reads the RECT bank), in a batch, and on ragged shapes."""
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    fe640.set_gftt(True)
+    try:
+        fe640.submit_rect(0, golden["rect_l"], golden["rect_r"]); b = fe640.wait()
+        e, m = fe640.receive_eigen(b)
+        want, wmax = oracle.gftt_eig(golden["rect_l"])
+        assert np.array_equal(e[0], want) and int(m[0]) == wmax
+        d = fe640.receive_disp(b)[0]                                   # the BM result is unaffected
+        assert np.array_equal(d, oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=64))
+    finally:
+        fe640.set_gftt(False)
+    with pytest.raises(u.U96Error):                                    # bank filled without GFTT: nothing to receive
+        fe640.submit_rect(1, golden["rect_l"], golden["rect_r"]); fe640.wait(); fe640.receive_eigen(1)
+    rng = np.random.default_rng(11)
+    for (W, H, n) in ((640, 480, 5), (53, 37, 3), (130, 9, 2), (1242, 375, 2)):
+        L = rng.integers(0, 256, (n, H, W), dtype=np.uint8); L[0] = (np.kron(rng.integers(0, 2, (H // 3 + 1, W // 3 + 1)), np.ones((3, 3))) * 255).astype(np.uint8)[:H, :W]
+        R = rng.integers(0, 256, (n, H, W), dtype=np.uint8)
+        with u.StereoFrontEnd(0, W, H, n) as fe:
+            D = 32 if W < 200 else 64
+            fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=5, num_disparities=D, x_store_offset=1)
+            fe.set_gftt(True)
+            fe.submit_rect(0, L, R); b = fe.wait()
+            e, m = fe.receive_eigen(b)
+            for i in range(n):
+                want, wmax = oracle.gftt_eig(L[i])
+                assert np.array_equal(e[i], want), (W, H, i)
+                assert int(m[i]) == wmax
+    # sensor path: the map is computed from the RECTIFIED left image
+    L, R = u.synth_batch(1, 0, 2, 640, 480, 64)
+    fe640.set_rect_params(u.SHIPPED_RECT_PARAMS); fe640.set_gftt(True)
+    try:
+        fe640.submit_raw(0, L, R); b = fe640.wait()
+        rl, _ = fe640.receive_rect(b); e, m = fe640.receive_eigen(b)
+        for i in range(2):
+            want, wmax = oracle.gftt_eig(rl[i])
+            assert np.array_equal(e[i], want) and int(m[i]) == wmax
+    finally:
+        fe640.set_gftt(False)

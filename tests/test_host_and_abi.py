@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(libpath):
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
     lib.u96_abi_version.restype = ctypes.c_int
-    assert lib.u96_abi_version() == 3
+    assert lib.u96_abi_version() == 4
     lib.u96_strerror.restype = ctypes.c_char_p
     assert b"fallback" in lib.u96_strerror(-6)
 

@@ -238,3 +238,54 @@ def test_rect_registers_from_calibration(oracle):
         v = np.stack([(xs - Kn[2]) / Kn[0], (ys - Kn[3]) / Kn[1], np.ones_like(xs)], -1) @ Rr[cam]      # R^T applied to each ray
         wx = v[..., 0] / v[..., 2] * K[cam][0] + round(K[0][2]); wy = v[..., 1] / v[..., 2] * K[cam][1] + round(K[0][3])
         assert np.abs(mx / 32.0 - wx).max() < 0.06 and np.abs(my / 32.0 - wy).max() < 0.06
+
+
+def _gftt_numpy(img):
+    """Independent vectorised reading of dvp/rtl/gftt_{sbl,eig,box,obuf}.v (second restatement, int64 numpy)."""
+    p = img.astype(np.int64); H, W = p.shape
+    dx = np.zeros((H, W), np.int64); dy = np.zeros((H, W), np.int64)
+    dx[1:-1, 1:-1] = (p[:-2, 2:] - p[:-2, :-2]) + 2 * (p[1:-1, 2:] - p[1:-1, :-2]) + (p[2:, 2:] - p[2:, :-2])
+    dy[1:-1, 1:-1] = (p[2:, :-2] - p[:-2, :-2]) + 2 * (p[2:, 1:-1] - p[:-2, 1:-1]) + (p[2:, 2:] - p[:-2, 2:])
+    ax, ay = np.abs(dx), np.abs(dy)
+
+    def box(v):
+        h = np.zeros_like(v)
+        h[:, 1:-1] = v[:, :-2] + v[:, 1:-1] + v[:, 2:]          # columns 0 and W-1 forced to 0 (gftt_box.v:185)
+        s = np.zeros_like(v)
+        s[2:-2] = h[1:-3] + h[2:-2] + h[3:-1]
+        return np.minimum(s, 0xFFFF)
+
+    a, c, b = box((ax * ax) >> 6), box((ay * ay) >> 6), box((ax * ay) >> 6)
+    s = np.minimum(((a - c) ** 2 >> 10) + ((b * b) >> 8), 0x3FFFFF) << 10
+    root = np.floor(np.sqrt(s.astype(np.float64))).astype(np.int64)
+    root = np.where(root * root > s, root - 1, root); root = np.where((root + 1) ** 2 <= s, root + 1, root)
+    e = (a + c) - (root & 0xFFFF)
+    out = np.where(e < 0, 0, np.where(e & 0x10000, 0xFFFF, e)).astype(np.uint16)
+    out[:2] = 0; out[-2:] = 0
+    return out
+
+
+def test_gftt_oracle_agrees_with_independent_numpy_reading(oracle, golden):
+    """the reference ships no eigen dump (parity unpinned); two independent readings of the RTL agree,
+    and the structural facts of the RTL hold: border rows/columns are zero, max = gftt.Max over the written rows."""
+    rng = np.random.default_rng(5)
+    imgs = [golden["rect_l"], golden["rect_r"], rng.integers(0, 256, (37, 53), dtype=np.uint8),
+            (np.kron(rng.integers(0, 2, (14, 22)), np.ones((3, 3))) * 255).astype(np.uint8)]   # 0/255 blocks drive the 16/22-bit limits
+    for img in imgs:
+        got, mx = oracle.gftt_eig(img)
+        assert np.array_equal(got, _gftt_numpy(img))
+        assert mx == int(got.max())
+        assert not got[:2].any() and not got[-2:].any() and not got[:, 0].any() and not got[:, -1].any()
+    assert oracle.gftt_eig(np.full((16, 16), 77, np.uint8))[1] == 0                 # flat image: no corners
+    assert oracle.gftt_eig(imgs[3])[1] == 0xFFFF                                    # the output limiter is reached
+
+
+def test_gftt_map_tracks_opencv_min_eigenvalue(oracle, golden):
+    """Sanity against the algorithm the RTL approximates (cv::cornerMinEigenVal, blockSize 3, Sobel 3): the maps are
+    strongly rank-correlated on the reference's bundled image (not equal: the RTL drops the sign of dx*dy and truncates)."""
+    cv2 = pytest.importorskip("cv2")
+    img = golden["rect_l"]
+    got = oracle.gftt_eig(img)[0][2:-2, 1:-1].astype(np.float64).ravel()
+    ref = cv2.cornerMinEigenVal(img, 3, ksize=3)[2:-2, 1:-1].astype(np.float64).ravel()
+    top = ref >= np.quantile(ref, 0.99)
+    assert np.mean(got[top] >= np.quantile(got, 0.95)) > 0.9

@@ -63,6 +63,10 @@ int launch_reproject(const int16_t *disp, int dpitch, size_t dframe, int W, int 
 int launch_pack_uvc(const uint8_t *srcL, const uint8_t *srcR, int sp, size_t sf, const int16_t *disp, int dp, size_t df,
                     uint8_t *out, int W, int H, int n, cudaStream_t s);
 
+// GFTT min-eigenvalue map (dvp/rtl/gftt*.v) of one image per frame: u16 map + per-frame maximum; returns kernels launched
+int launch_gftt(const uint8_t *src, int sp, size_t sf, uint16_t *eig, int ep, size_t ef, uint32_t *fmax,
+                int W, int H, int n, cudaStream_t s);
+
 int run_microbench(int which, double *gops);
 
 }  // namespace u96

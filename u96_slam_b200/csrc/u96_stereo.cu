@@ -8,6 +8,7 @@
 #include <deque>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -42,6 +43,9 @@ struct Bank {
     int16_t *cost = nullptr;            // OPENCV post filters: winning SAD per pixel (lazy)
     int *cc = nullptr;                  // filterSpeckles: label + size, 2 int32 per pixel of a batch (lazy, per bank)
     size_t cc_cap = 0;
+    uint16_t *eig = nullptr;            // GFTT min-eigenvalue map (lazy), same pitch (in elements) as the u8 images
+    uint32_t *eig_max = nullptr;        // per-frame maximum (gftt.Max)
+    bool has_eig = false;
     // where the current contents of each stage live (internal buffer or a caller's device pointer)
     const uint8_t *cur_raw[2] = {nullptr, nullptr}, *cur_rect[2] = {nullptr, nullptr}, *cur_xsbl[2] = {nullptr, nullptr};
     int raw_pitch = 0, rect_pitch = 0, xsbl_pitch = 0;
@@ -67,7 +71,7 @@ struct u96_handle {
     Bank bank[2];
     std::deque<int> fifo;
     cudaStream_t user_stream = nullptr;
-    bool use_user_stream = false, profiling = false;
+    bool use_user_stream = false, profiling = false, gftt = false;
     int64_t launches = 0;
     float *xyz = nullptr;
     size_t xyz_cap = 0;
@@ -186,6 +190,8 @@ void u96_destroy(u96_handle *h)
         cudaFree(k.disp);
         cudaFree(k.cost);
         cudaFree(k.cc);
+        cudaFree(k.eig);
+        cudaFree(k.eig_max);
         if (k.done) cudaEventDestroy(k.done);
         for (int i = 0; i < 5; i++) if (k.ev[i]) cudaEventDestroy(k.ev[i]);
         for (int i = 0; i < 3; i++) { if (k.sub_ev[i]) cudaEventDestroy(k.sub_ev[i]); if (k.sub[i]) { cudaStreamSynchronize(k.sub[i]); cudaStreamDestroy(k.sub[i]); } }
@@ -248,6 +254,13 @@ int u96_set_stream(u96_handle *h, void *cuda_stream)
     return U96_OK;
 }
 
+int u96_set_gftt(u96_handle *h, int enable)
+{
+    if (!h) return U96_ERR_INVALID;
+    h->gftt = enable != 0;
+    return U96_OK;
+}
+
 int u96_set_profiling(u96_handle *h, int on)
 {
     if (!h) return U96_ERR_INVALID;
@@ -289,6 +302,9 @@ static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStrea
     if (from == FROM_RAW)
         h->launches += launch_rect_remap(k.cur_raw[0] + (size_t)f0 * k.raw_frame, k.cur_raw[1] + (size_t)f0 * k.raw_frame, k.raw_pitch,
                                          k.raw_frame, rectL, rectR, h->map, h->plan, W, H, nf, s);
+    if (h->gftt && from <= FROM_RECT)                        // the GFTT block reads the RECT bank (fpga.c:166-167)
+        h->launches += launch_gftt(k.cur_rect[0] + (size_t)f0 * k.rect_frame, k.rect_pitch, k.rect_frame, k.eig + o, pitch, frame,
+                                   k.eig_max + f0, W, H, nf, s);
     if (prof) CK(cudaEventRecord(k.ev[2], s));
     if (from <= FROM_RECT)
         h->launches += launch_xsobel(k.cur_rect[0] + (size_t)f0 * k.rect_frame, k.cur_rect[1] + (size_t)f0 * k.rect_frame, k.rect_pitch,
@@ -355,6 +371,11 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
             k.cc_cap = need;
         }
     }
+    if (h->gftt && from <= FROM_RECT && !k.eig) {
+        if (cudaMalloc(&k.eig, (size_t)pitch * H * h->maxB * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMalloc(&k.eig_max, (size_t)h->maxB * sizeof(uint32_t)) != cudaSuccess) return U96_ERR_NOMEM;
+    }
+    k.has_eig = h->gftt && from <= FROM_RECT;
     const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= 64;
     if (!pipelined) {
         if (!zero_copy)
@@ -474,6 +495,22 @@ int u96_receive_disp(u96_handle *h, int bank, int16_t *disp)
     return U96_OK;
 }
 
+int u96_receive_eigen(u96_handle *h, int bank, uint16_t *eig, uint16_t *max_eig)
+{
+    if (!h || bank < 0 || bank > 1 || !eig) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!k.filled || !k.has_eig) return U96_ERR_STATE;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    const int W = h->bm.width, H = h->bm.height;
+    CK(copy2d(eig, (size_t)W * 2, k.eig, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n, cudaMemcpyDeviceToHost, s));
+    std::vector<uint32_t> mx(max_eig ? k.n : 0);
+    if (max_eig) CK(cudaMemcpyAsync(mx.data(), k.eig_max, (size_t)k.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < (int)mx.size(); i++) max_eig[i] = (uint16_t)mx[i];
+    return U96_OK;
+}
+
 int u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp)
 {
     if (!h || bank < 0 || bank > 1 || !disp) return U96_ERR_INVALID;
@@ -549,6 +586,7 @@ int u96_bank_device_ptr(u96_handle *h, int bank, int which, void **dptr, int *pi
     case U96_BUF_RECT_L: case U96_BUF_RECT_R: p = k.rect[which - U96_BUF_RECT_L]; break;
     case U96_BUF_XSBL_L: case U96_BUF_XSBL_R: p = k.xsbl[which - U96_BUF_XSBL_L]; break;
     case U96_BUF_DISP: p = k.disp; pitch *= 2; frame *= 2; break;
+    case U96_BUF_EIG: p = k.eig; pitch *= 2; frame *= 2; break;
     }
     *dptr = const_cast<void *>(p);
     if (pitch_bytes) *pitch_bytes = pitch;

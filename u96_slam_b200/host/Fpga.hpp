@@ -100,6 +100,18 @@ public:
         matDepth = std::move(d);
         return 0;
     }
+    // fpga->gftt.Control = FPGA_GFTT_CTRL_ENABLE (StereoBM/src/fpga.c:162-172)
+    int enableGftt(bool on) { return u96_set_gftt(h_, on ? 1 : 0) == U96_OK ? 0 : -1; }
+    // FPGA.cpp:281-296 -- CV_16UC1 min-eigenvalue map + the bank's half of reg->gftt.Max
+    int receiveEigen(int bank, std::vector<uint16_t> &matEigen, unsigned short *maxEigen)
+    {
+        std::vector<uint16_t> e((size_t)IMAGE_HEIGHT * IMAGE_WIDTH);
+        uint16_t mx = 0;
+        if (u96_receive_eigen(h_, bank, e.data(), &mx) != U96_OK) return -1;
+        matEigen = std::move(e);
+        if (maxEigen) *maxEigen = mx;
+        return 0;
+    }
     // FPGA.cpp:310-347 (stereo part): wait, then copy the active bank out
     int receiveData(Mat8 &rectLeft, Mat8 &rectRight, Mat16 &depth)
     {

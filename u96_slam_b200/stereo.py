@@ -94,6 +94,8 @@ def load_library():
     L.u96_receive_xsbl.argtypes = [vp, i32, u8p, u8p]
     L.u96_receive_disp.argtypes = [vp, i32, vp]
     L.u96_receive_uvc.argtypes = [vp, i32, i32, vp]
+    L.u96_set_gftt.argtypes = [vp, i32]
+    L.u96_receive_eigen.argtypes = [vp, i32, vp, vp]
     L.u96_enqueue_receive_disp.argtypes = [vp, i32, vp]
     L.u96_reproject.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), i32, i32, vp]
     L.u96_bank_device_ptr.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_size_t)]
@@ -238,6 +240,17 @@ class StereoFrontEnd:
         _check(self.L, self.L.u96_receive_disp(self.h, bank, d.ctypes.data), "u96_receive_disp")
         return d
 
+    def set_gftt(self, on=True):
+        """fpga->gftt.Control = FPGA_GFTT_CTRL_ENABLE (fpga.c:162-172)"""
+        _check(self.L, self.L.u96_set_gftt(self.h, 1 if on else 0), "u96_set_gftt")
+
+    def receive_eigen(self, bank):
+        """Fpga::receiveEigen (FPGA.cpp:281-296): (n, H, W) u16 min-eigenvalue map, (n,) u16 per-frame maxima (gftt.Max)"""
+        n = self._n[bank]
+        e = np.empty((n, self.H, self.W), np.uint16); m = np.empty(n, np.uint16)
+        _check(self.L, self.L.u96_receive_eigen(self.h, bank, e.ctypes.data, m.ctypes.data), "u96_receive_eigen")
+        return e, m
+
     def receive_uvc(self, bank, which):
         """UVC payload of the firmware (xusb_main.c:293-376): (n, H, 2W, 2) u8 YUYV; which = UVC_RECT / UVC_XSBL / UVC_BM"""
         n = self._n[bank]
@@ -334,6 +347,15 @@ class Fpga:
 
     def receiveDepthMap(self, bank):
         return self.fe.receive_disp(bank)[0]
+
+    def enableGftt(self, on=True):
+        """fpga->gftt.Control = FPGA_GFTT_CTRL_ENABLE when RETURN_DATA_GFTT is requested (fpga.c:162-172)"""
+        self.fe.set_gftt(on)
+
+    def receiveEigen(self, bank):
+        """FPGA.cpp:281-296 -> (CV_16UC1 map, maxEigen)"""
+        e, m = self.fe.receive_eigen(bank)
+        return e[0], int(m[0])
 
     def receiveData(self):
         """-> (activeBank, rectL, rectR, disparity CV_16SC1)"""
