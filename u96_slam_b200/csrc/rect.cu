@@ -438,7 +438,8 @@ int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, s
         if (encode_src_map(&tmL, srcL, src_pitch, src_frame, W, H, n, pl.BW, pl.BH) &&
             encode_src_map(&tmR, srcR, src_pitch, src_frame, W, H, n, pl.BW, pl.BH)) {
             const int nt = pl.tiles_x * pl.tiles_y;
-            const int fpb = 16;
+            static const int fpb_env = getenv("U96_RECT_FPB") ? atoi(getenv("U96_RECT_FPB")) : 0;
+            const int fpb = fpb_env > 0 ? fpb_env : 32;
             const int smem = RT_STAGES * pl.stage_bytes + 2 * RT_STAGES * (int)sizeof(uint64_t);
             cudaFuncSetAttribute(k_rect_remap_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_STAGES * 16384 + 128);
             dim3 grid(nt, 2, (n + fpb - 1) / fpb);

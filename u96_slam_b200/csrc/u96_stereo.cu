@@ -5,6 +5,7 @@
 // (RECT, XSBL, DISP; StereoBM/src/fpga.h:50-68), fills a bank asynchronously on submit and copies
 // results out on receive.  There is no CPU code path: every stage is a CUDA kernel.
 #include <algorithm>
+#include <cstdlib>
 #include <deque>
 #include <new>
 #include <string>
@@ -390,7 +391,9 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     } else {
         // chunks of whole BM waves (a chunk that fills half the SMs would make the kernels, not PCIe, the bottleneck)
         const int wave = bm_wave_frames(bm_config(h->bm));
-        int csz = std::max(wave, (32 + wave - 1) / wave * wave);
+        int csz = std::max(2 * wave, (32 + wave - 1) / wave * wave);     // two waves per chunk: measured best against the PCIe ceiling
+        static const int csz_env = getenv("U96_CHUNK") ? atoi(getenv("U96_CHUNK")) : 0;     // developer override (frames per chunk)
+        if (csz_env > 0) csz = csz_env;
         if (csz > n) csz = n;
         CK(cudaEventRecord(k.done, s));                       // the sub-streams start behind whatever the bank stream holds
         for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(k.sub[i], k.done, 0));
