@@ -474,3 +474,47 @@ def test_gftt_min_eigenvalue_map(u, fe640, golden, oracle):
             assert np.array_equal(e[i], want) and int(m[i]) == wmax
     finally:
         fe640.set_gftt(False)
+
+
+def test_randomised_shapes_and_parameters_both_profiles(u, oracle):
+    """Seeded sweep over ragged widths/heights, window sizes, disparity ranges (fast path, cluster path and the generic
+    kernel), uniqueness settings and both profiles, on noise images (ties, saturation, flat areas): bit-exact every time."""
+    rng = np.random.default_rng(20261017)
+    cases = []
+    for _ in range(14):
+        D = int(rng.choice([32, 64, 96, 128, 160, 256]))
+        B = int(rng.choice([5, 7, 9, 11, 15, 17, 21, 25, 31]))
+        W = int(D + B + 2 + rng.integers(3, 260)); H = int(B + rng.integers(1, 70))
+        cases.append((W, H, D, B))
+    cases += [(64 + 21 + 2, 21, 64, 21), (64 + 31 + 3, 31, 64, 31), (777, 33, 128, 9)]       # minimal valid sizes, one centre column
+    for i, (W, H, D, B) in enumerate(cases):
+        kind = i % 3
+        if kind == 0:                                   # noise
+            L = rng.integers(0, 256, (2, H, W), dtype=np.uint8); R = rng.integers(0, 256, (2, H, W), dtype=np.uint8)
+        elif kind == 1:                                 # flat areas + a few edges: ties everywhere
+            L = np.full((2, H, W), 90, np.uint8); R = np.full((2, H, W), 90, np.uint8)
+            L[:, :, W // 3:] = 200; R[:, :, W // 2:] = 200; L[1, H // 2:] = 10
+        else:                                           # 0/255 blocks: column sums saturate at 10 bit
+            L = (np.kron(rng.integers(0, 2, (2, H // 2 + 1, W // 2 + 1)), np.ones((2, 2))) * 255).astype(np.uint8)[:, :H, :W]
+            R = np.roll(L, -int(rng.integers(0, D)), axis=2)
+        with u.StereoFrontEnd(0, W, H, 2) as fe:
+            uni = int(rng.integers(0, 2)); thr = int(rng.integers(0, 1024)); mode = int(rng.integers(0, 2)); ext = int(D > 128 or rng.integers(0, 2))
+            xo = int(rng.integers(0, 2))
+            fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=B, num_disparities=D, uni_enable=uni, uni_thr=thr,
+                             uni_mode=mode, rtl_extended=ext, x_store_offset=xo)
+            fe.submit_rect(0, L, R); b = fe.wait()
+            d = fe.receive_disp(b); sl, sr = fe.receive_xsbl(b)
+            for k in range(2):
+                xl, xr = oracle.xsobel_rtl(L[k]), oracle.xsobel_rtl(R[k])
+                assert np.array_equal(sl[k], xl) and np.array_equal(sr[k], xr), ("xsbl", W, H)
+                want = oracle.bm_rtl(xl, xr, wsz=B, ndisp=D, uni_enb=uni, uni_thr=thr, uni_mode=mode, rtl_extended=ext, x_store_offset=xo)
+                assert np.array_equal(d[k], want), ("rtl", W, H, D, B, uni, thr, mode, ext, xo, int((d[k] != want).sum()))
+            if B >= 5 and B * B * 62 <= 65535:
+                cap = int(rng.integers(1, 32)); tex = int(rng.integers(0, 40)); uq = int(rng.integers(0, 30))
+                fe.set_bm_params(profile=u.PROFILE_OPENCV, prefilter_cap=cap, texture_threshold=tex, uniqueness_ratio=uq)
+                fe.submit_rect(1, L, R); b = fe.wait()
+                d = fe.receive_disp(b)
+                for k in range(2):
+                    want = oracle.bm_cv(oracle.xsobel_cv(L[k], cap), oracle.xsobel_cv(R[k], cap), wsz=B, ndisp=D, prefilter_cap=cap,
+                                        texture_threshold=tex, uniqueness_ratio=uq)
+                    assert np.array_equal(d[k], want), ("cv", W, H, D, B, cap, tex, uq, int((d[k] != want).sum()))
