@@ -70,23 +70,30 @@ __global__ void __launch_bounds__(128) k_gftt_eig(const uint8_t *__restrict__ sr
 #pragma unroll
         for (int j = 0; j < GF_PX; j++) hm[j] = (x0 + j >= 1 && x0 + j <= W - 2) ? 0xFFFFFFFFu : 0u;
 
+        // the three aligned words around columns x0..x0+3 of an input row (zero outside the row; those columns only feed
+        // masked taps); rows past the image are never consumed
+        auto fetch_row = [&](int y, uint32_t (&q)[3]) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(img + (size_t)min(y, H - 1) * sp);
+            q[0] = (wc > 0) ? __ldg(row + wc - 1) : 0u;
+            q[1] = __ldg(row + wc);
+            q[2] = (wc + 1 < pw) ? __ldg(row + wc + 1) : 0u;
+        };
         // widened row (columns x0-2..x0+5) and its horizontal 1-2-1 sums at columns x0-1..x0+4
-        auto load_row = [&](int y, uint32_t (&w)[4], uint32_t (&g)[3]) {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(img + (size_t)y * sp);
-            const uint32_t wl = (wc > 0) ? __ldg(row + wc - 1) : 0u;
-            const uint32_t wm = __ldg(row + wc);
-            const uint32_t wr = (wc + 1 < pw) ? __ldg(row + wc + 1) : 0u;
-            w[0] = __byte_perm(wl, 0, 0x4342); w[1] = __byte_perm(wm, 0, 0x4140);
-            w[2] = __byte_perm(wm, 0, 0x4342); w[3] = __byte_perm(wr, 0, 0x4140);
+        auto widen_row = [&](const uint32_t (&q)[3], uint32_t (&w)[4], uint32_t (&g)[3]) {
+            w[0] = __byte_perm(q[0], 0, 0x4342); w[1] = __byte_perm(q[1], 0, 0x4140);
+            w[2] = __byte_perm(q[1], 0, 0x4342); w[3] = __byte_perm(q[2], 0, 0x4140);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const uint32_t o = __byte_perm(w[j], w[j + 1], 0x5432);      // odd pair
                 g[j] = w[j] + 2u * o + w[j + 1];                             // <= 1020 per half
             }
         };
+        auto load_row = [&](int y, uint32_t (&w)[4], uint32_t (&g)[3]) { uint32_t q[3]; fetch_row(y, q); widen_row(q, w, g); };
         uint32_t wr[3][4], gr[3][3];                       // ring of the last three input rows (slot = row mod 3, compile time)
         load_row(ys - 2, wr[0], gr[0]);
         load_row(ys - 1, wr[1], gr[1]);
+        uint32_t nx[3];                                    // input row y+1 of the coming step, requested one step ahead
+        fetch_row(ys, nx);
         uint32_t hs[3][3][GF_PX];                          // [row slot][dx2, dy2, dxdy][column]: horizontal 3-sums (<= 48768)
 #pragma unroll
         for (int s = 0; s < 3; s++)
@@ -100,7 +107,8 @@ __global__ void __launch_bounds__(128) k_gftt_eig(const uint8_t *__restrict__ sr
         auto step = [&](const int y, auto slot_c, auto edge_c) {
             constexpr int slot = decltype(slot_c)::value, i0 = slot, i1 = (slot + 1) % 3, i2 = (slot + 2) % 3;
             constexpr bool EDGE = decltype(edge_c)::value;
-            load_row(y + 1, wr[i2], gr[i2]);
+            widen_row(nx, wr[i2], gr[i2]);
+            fetch_row(y + 2, nx);                          // in flight during this step's arithmetic
             uint32_t sv[4];                                // vertical 1-2-1 sums, columns x0-2..x0+5
 #pragma unroll
             for (int j = 0; j < 4; j++) sv[j] = wr[i0][j] + 2u * wr[i1][j] + wr[i2][j];
