@@ -10,7 +10,10 @@
  *   - x-Sobel (RTL):   pinned bit-exact by the reference's own golden vectors
  *                      data/ref_rect_{l,r} -> data/ref_xsbl_{l,r}.
  *   - rect_remap:      pinned against the reference's own C function compiled
- *                      from where it lies (oracle/_ref, fpga.c:303-366).
+ *                      from where it lies (oracle/_ref, fpga.c:303-366); that
+ *                      build also regenerates the shipped src/dvp/sim/cmd.dat.
+ *   - GFTT map:        PARITY UNPINNED (no eigen dump shipped; CORDIC sqrt IP
+ *                      modelled as exact truncation); two readings agree.
  *   - diven closed forms: pinned against a bit-serial emulation of diven.v.
  *   - cv::StereoBM profile: pinned against cv2.StereoBM 4.13 (the third-party
  *                      library the reference calls; version unpinned upstream).

@@ -81,6 +81,9 @@ def main():
     m = ref.rect_remap(SHIPPED_RECT, 640, 480)
     np.savez_compressed(os.path.join(HERE, "rect_remap_ref.npz"),
                         xs_l=m[0][0], ys_l=m[0][1], xs_r=m[1][0], ys_r=m[1][1])
+    # the reference's shipped rectifier command dump (src/dvp/sim/cmd.dat, read by the testbench sim_dvp.v:174)
+    words = np.array([int(t, 16) for t in open(os.path.join(REF, "src", "dvp", "sim", "cmd.dat")).read().split()], np.uint32)
+    np.savez_compressed(os.path.join(HERE, "rect_cmd_dat.npz"), words=words)
     print("golden fixtures written")
 
 

@@ -264,4 +264,20 @@ class RefFpga:
                 m.data[k] = a[k].ctypes.data_as(ctypes.POINTER(ctypes.c_short))
             maps.append(m); bufs.append(a)
         self.L.rect_remap(ctypes.byref(p), ctypes.byref(maps[0]), ctypes.byref(maps[1]))
+        self._last = (p, maps, bufs)
         return bufs
+
+    def rect_cmd_stream(self, d, W, H):
+        """rect_remap() + rect_cmd_gen() of the reference (fpga.c:303-605): the 18-bit words issue_cmd() writes to the
+        rectifier's command port, captured by oracle/ref_stubs/capture_cmd.h."""
+        self.rect_remap(d, W, H)
+        p, maps, _ = self._last
+        L = self.L
+        L.set_rect_param.argtypes = [ctypes.POINTER(_RefRectParam)]; L.set_rect_param.restype = None
+        L.rect_cmd_gen.argtypes = [_RefMat2S, _RefMat2S]; L.rect_cmd_gen.restype = None
+        L.u96_ref_cmd_data.restype = ctypes.POINTER(ctypes.c_uint)
+        L.set_rect_param(ctypes.byref(p))
+        L.u96_ref_cmd_reset()
+        L.rect_cmd_gen(maps[0], maps[1])
+        n = L.u96_ref_cmd_count()
+        return np.ctypeslib.as_array(L.u96_ref_cmd_data(), shape=(n,)).astype(np.uint32)

@@ -5,7 +5,7 @@ import zlib
 import numpy as np
 import pytest
 
-from oracle_py import SHIPPED_RECT, REF_LIB_PATH
+from oracle_py import SHIPPED_RECT, REF_LIB_PATH, RefFpga
 
 
 def test_kat1_xsobel_matches_reference_golden(oracle, golden):
@@ -31,6 +31,38 @@ def test_rect_remap_matches_reference_function(oracle):
         assert np.array_equal(xs, m["xs_" + n]) and np.array_equal(ys, m["ys_" + n])
     # shipped parameters map inside the source image
     assert xs.min() >= 0 and xs.max() < 640 * 32 and ys.min() >= 0 and ys.max() < 480 * 32
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIB_PATH), reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_command_stream_reproduces_shipped_cmd_dat(oracle):
+    """KAT from the reference's own assets: rect_remap() + rect_cmd_gen() of the reference's fpga.c, compiled
+    from where it lies and run on the shipped parameter set, regenerate src/dvp/sim/cmd.dat (17 104 words) exactly once the
+    firmware's 4 KiB-boundary burst split (issue_cmd, fpga.c:519-541, absent from the testbench dump) is undone.  The
+    stream encodes, per destination row, the source-row transitions and span lengths of the inverse map, so this pins the
+    compiled reference map -- which the oracle's orc_rect_remap equals bit for bit (previous tests) -- to a reference file."""
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", "rect_cmd_dat.npz"))["words"]
+    got = RefFpga().rect_cmd_stream(SHIPPED_RECT, 640, 480)
+    merged, splits, ydst = [], 0, 0
+    for v in (int(x) for x in got):
+        if not v & 0xFF:                                # Y command: {lr[17], ydst[16:8]}
+            ydst = (v >> 8) & 0x1FF
+            merged.append(v)
+        elif (merged[-1] & 0xFF) and not (v >> 7) & 1 and (v >> 8) == (merged[-1] >> 8) + (merged[-1] & 0x7F) \
+                and (ydst * 640 + (v >> 8)) % 4096 == 0:
+            merged[-1] += v & 0x7F                      # second half of a burst that crossed a 4 KiB boundary
+            splits += 1
+        else:
+            ydst += (v >> 7) & 1                        # ydif: the destination row advances (cmd_x, fpga.c:572-603)
+            merged.append(v)
+    assert len(got) == len(want) + splits and splits > 0
+    assert np.array_equal(np.array(merged, np.uint32), want)
+    # the implicit contract the GPU path keeps from the command stream (SURVEY a4): every destination pixel exactly once
+    assert sum(v & 0x7F for v in merged if v & 0xFF) == 2 * 640 * 480
+    # and the map the stream was generated from is the oracle's map
+    ref = RefFpga().rect_remap(SHIPPED_RECT, 640, 480)
+    for lr in (0, 1):
+        xs, ys = oracle.rect_remap(SHIPPED_RECT, lr, 640, 480)
+        assert np.array_equal(xs, ref[lr][0]) and np.array_equal(ys, ref[lr][1])
 
 
 @pytest.mark.skipif(not os.path.exists(REF_LIB_PATH), reason="oracle/_ref not built (no /root/reference here)")
