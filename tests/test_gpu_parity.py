@@ -254,6 +254,7 @@ def test_cpp_host_shim(u):
         assert int(f[3]) == i % 2                                    # bank = iteration % 2 (main.cpp:168)
         assert float(f[f.index("frac_at_12px") + 1]) > 0.95          # random texture shifted by 12 px
         assert int(f[-1]) > 10000                                    # dense points from the x4-decimated map
+        assert 0 < int(f[f.index("eig_max") + 1]) <= 0xFFFF and int(f[f.index("candidates") + 1]) > 1000   # receiveEigen (FPGA.cpp:281-296)
 
 
 def test_async_receive_pipeline(u, oracle):

@@ -19,6 +19,7 @@ int main(int argc, char **argv)
     const double P_l[12] = {718.856 * sx, 0, 607.1928 * sx, 0, 0, 718.856 * sy, 185.2157 * sy, 0, 0, 0, 1, 0};
     double P_r[12]; for (int i = 0; i < 12; i++) P_r[i] = P_l[i]; P_r[3] = -386.1448 * sx;
     uint64_t seed = 1;
+    if (fpga.enableGftt(true) != 0) return 6;                           // RETURN_DATA_GFTT: fpga.c:162-172
     for (int it = 0; it < frames; it++) {
         u96::Mat8 L(480, 640), R(480, 640);
         for (int y = 0; y < 480; y++)                                   // textured pair with a 12-pixel shift
@@ -39,8 +40,14 @@ int main(int argc, char **argv)
         long long sum = 0, valid = 0, at12 = 0;
         for (short s : depth.data) { if (s >= 0) { valid++; sum += s; at12 += (s >= 11 * 16 && s <= 13 * 16); } }
         int pts = 0; for (size_t i = 0; i < xyz.size(); i += 3) pts += (xyz[i] == xyz[i]);
-        printf("frame %d bank %d valid %lld mean_disp %.3f frac_at_12px %.3f decimated %dx%d points %d\n", it, active, valid,
-               valid ? sum / 16.0 / valid : 0.0, valid ? (double)at12 / valid : 0.0, small.cols, small.rows, pts);
+        // keypoint branch (main.cpp:236-243): eigen map + gftt.Max, then the threshold of generateKeypoints2 (GFTT.cpp:56-68)
+        std::vector<uint16_t> eig; unsigned short maxEigen = 0;
+        if (fpga.receiveEigen(active, eig, &maxEigen) != 0) return 7;
+        const double thr = maxEigen * 0.01;
+        int cand = 0;
+        for (int y = 1; y < 479; y++) for (int x = 1; x < 639; x++) cand += ((float)eig[(size_t)y * 640 + x] >= thr);
+        printf("frame %d bank %d valid %lld mean_disp %.3f frac_at_12px %.3f decimated %dx%d eig_max %u candidates %d points %d\n", it, active,
+               valid, valid ? sum / 16.0 / valid : 0.0, valid ? (double)at12 / valid : 0.0, small.cols, small.rows, (unsigned)maxEigen, cand, pts);
     }
     return 0;
 }
