@@ -360,6 +360,9 @@ def main():
             cv = cpu_cv2_reference(wl, 32, cores)
             if cv is not None:
                 cpu["cv2_stereobm_frames_per_s"] = cv
+                cpu["cv2_stereobm_1thread_frames_per_s"] = cpu_cv2_reference(wl, 12, 1)      # 1 thread and nproc
+            cpu["port_1thread_frames_per_s"] = cpu_oracle_baseline(wl, 2, 1)
+            cpu["cpu_model"] = next((ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")), "unknown")
         line = {"metric": "disparity_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
