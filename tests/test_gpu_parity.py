@@ -277,21 +277,26 @@ def test_pipelined_async_submit_matches(u, oracle):
     """u96_submit_raw_async: chunked H2D / kernels / D2H pipeline gives the same bits as the plain path."""
     import torch
     L, R = u.synth_batch(1, 0, 4, 640, 480, 64)
-    n = 70                                                       # >= 64 -> chunked over the sub-streams
-    hL = torch.from_numpy(np.concatenate([L] * 18)[:n]).pin_memory(); hR = torch.from_numpy(np.concatenate([R] * 18)[:n]).pin_memory()
+    n = 310                                                      # three chunks (two BM waves = 148 frames each, then 14) over the sub-streams
+    reps = (n + 3) // 4
+    hL = torch.from_numpy(np.concatenate([L] * reps)[:n]).pin_memory(); hR = torch.from_numpy(np.concatenate([R] * reps)[:n]).pin_memory()
     out = torch.empty((n, 480, 640), dtype=torch.int16).pin_memory()
     with u.StereoFrontEnd(0, 640, 480, n) as fe:
         fe.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
         fe.set_bm_params(x_store_offset=1)
         fe.set_rect_params(u.SHIPPED_RECT_PARAMS)
+        fe.set_gftt(True)                                        # the eigen map is produced per chunk as well
         fe.submit_host_ptr_async("raw", 0, hL.data_ptr(), hR.data_ptr(), 640, n, out.data_ptr())
         assert fe.wait() == 0
         ref = fe.receive_disp(0)
         assert np.array_equal(out.numpy(), ref)
-        for i in (0, 1, 37, 69):
+        e, m = fe.receive_eigen(0)
+        for i in (0, 1, 147, 148, 149, 295, 296, 309):
             j = i % 4
             rl, rr = oracle.rectify(L[j], u.SHIPPED_RECT_PARAMS, 0), oracle.rectify(R[j], u.SHIPPED_RECT_PARAMS, 1)
-            assert np.array_equal(out[i].numpy(), oracle.bm_rtl(oracle.xsobel_rtl(rl), oracle.xsobel_rtl(rr), wsz=21, ndisp=64))
+            assert np.array_equal(out[i].numpy(), oracle.bm_rtl(oracle.xsobel_rtl(rl), oracle.xsobel_rtl(rr), wsz=21, ndisp=64)), i
+            we, wm = oracle.gftt_eig(rl)
+            assert np.array_equal(e[i], we) and int(m[i]) == wm, i
 
 
 def test_c5_slam_loop_octomap(u, oracle, tmp_path):
