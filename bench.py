@@ -322,6 +322,24 @@ def main():
                 "note": "pinned H2D of the step's inputs and D2H of its disparity maps issued together, no kernels"}
         del dI, dO
 
+    # single-pair latency through the reference-shaped calls (what one iteration of the slam loop pays: main.cpp:165-181)
+    latency = None
+    if rank == 0:
+        fe3 = u.StereoFrontEnd(local, W, H, 1)
+        configure(fe3)
+        l1, r1 = hL[:1].copy(), hR[:1].copy()
+        d1 = np.empty((1, H, W), np.int16)
+        ts = []
+        for i in range(40):
+            t0 = time.perf_counter()
+            fe3.submit_raw(i & 1, l1, r1)
+            b = fe3.wait()
+            fe3.receive_disp(b, out=d1)
+            ts.append(time.perf_counter() - t0)
+        fe3.close()
+        latency = {"ms_median": 1e3 * float(np.median(ts[8:])), "ms_p90": 1e3 * float(np.quantile(ts[8:], 0.9)),
+                   "what": "one host pair: u96_submit_raw + u96_wait + u96_receive_disp (pageable host buffers)"}
+
     if rank == 0:
         # ---- roofline of the dominant kernel (k_bm): integer pipe, measured issue rate as the peak ----
         int_peak = microbench(1, local) / 1e3            # VABSDIFF4 / ALU-pipe issue rate, T lane-op/s
@@ -374,7 +392,8 @@ def main():
                         "d2h_bytes_per_step": int(2 * W * H * nb), "steps": e2e_steps, "checksum": checksum,
                         "timing": "wall clock around u96_submit_raw_async/u96_wait over two banks, synchronize on both sides",
                         "pcie": pcie},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "single_pair_latency": latency}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
