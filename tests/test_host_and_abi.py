@@ -132,3 +132,28 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_projection_matrix_loaders(tmp_path):
+    """KITTI calib.txt and OpenCV-yml projection matrices (StereoCameraModel.cpp:19-122), incl. the 640x480 rescale."""
+    import u96_slam_b200 as u
+    k = tmp_path / "calib.txt"
+    k.write_text("P0: 7.188560000000e+02 0 6.071928000000e+02 0 0 7.188560000000e+02 1.852157000000e+02 0 0 0 1 0\n"
+                 "P1: 7.188560000000e+02 0 6.071928000000e+02 -3.861448000000e+02 0 7.188560000000e+02 1.852157000000e+02 0 0 0 1 0\n"
+                 "P2: 1 0 0 0 0 1 0 0 0 0 1 0\n")
+    Pl, Pr = u.load_projection_kitti(str(k))
+    sx, sy = 640.0 / 1241, 480.0 / 376
+    assert Pl.shape == (3, 4) and np.isclose(Pl[0, 0], 718.856 * sx) and np.isclose(Pl[1, 2], 185.2157 * sy)
+    assert np.isclose(Pr[0, 3], -386.1448 * sx) and Pr[2, 2] == 1.0
+    Pl2, _ = u.load_projection_kitti(str(k), do_resize=False)
+    assert Pl2[0, 0] == 718.856
+    yml = ("%YAML:1.0\n---\nimage_width: 1280\nimage_height: 960\ncamera_name: {n}\n"
+           "projection_matrix: !!opencv-matrix\n   rows: 3\n   cols: 4\n   dt: d\n"
+           "   data: [ 800., 0., 650., {tx}, 0., 800.,\n       470., 0., 0., 0., 1., 0. ]\n")
+    (tmp_path / "l.yml").write_text(yml.format(n="left", tx="0."))
+    (tmp_path / "r.yml").write_text(yml.format(n="right", tx="-96."))
+    Pl, Pr = u.load_projection_opencv_yml(str(tmp_path / "l.yml"), str(tmp_path / "r.yml"))
+    assert np.allclose(Pl, [[400, 0, 325, 0], [0, 400, 235, 0], [0, 0, 1, 0]]) and np.isclose(Pr[0, 3], -48.0)
+    (tmp_path / "bad.yml").write_text(yml.format(n="x", tx="0.").replace("cols: 4", "cols: 3"))
+    with pytest.raises(ValueError):
+        u.load_projection_opencv_yml(str(tmp_path / "bad.yml"), str(tmp_path / "r.yml"))

@@ -48,3 +48,55 @@ def rect_params_from_calibration(K_src, R_rect, K_new):
         R = np.asarray(R_rect[cam], dtype=np.float64).reshape(3, 3)
         p["rot"].append([[int(round(R[i, j] * 2.0**24)) for j in range(3)] for i in range(3)])
     return p
+
+
+# ---- projection-matrix files of the reference's camera model (slam/src/core/StereoCameraModel.cpp:19-122) --------------------
+def _resize_projection(P, size, do_resize):
+    """StereoCameraModel.cpp:108-119: scale fx, cx, Tx by 640/width and fy, cy, Ty by 480/height."""
+    P = [np.array(p, np.float64).reshape(3, 4) for p in P]
+    if do_resize:
+        sx, sy = 640.0 / size[0], 480.0 / size[1]
+        for p in P:
+            p[0, 0] *= sx; p[0, 2] *= sx; p[0, 3] *= sx
+            p[1, 1] *= sy; p[1, 2] *= sy; p[1, 3] *= sy
+    return P[0], P[1]
+
+
+def load_projection_kitti(path, do_resize=True):
+    """KITTI odometry `calib.txt` (left/right combined, StereoCameraModel.cpp:71-104): lines `P0: 12 doubles`, `P1: 12 doubles`;
+    the image size is not in the file and is assumed 1241x376 like the reference does.  -> (P_l, P_r) 3x4 float64, ready for
+    u96_reproject."""
+    P = {}
+    for ln in open(path):
+        k, _, rest = ln.partition(":")
+        if k.strip() in ("P0", "P1"):
+            v = [float(t) for t in rest.split()]
+            if len(v) != 12:
+                raise ValueError(f"{path}: {k.strip()} needs 12 values")
+            P[k.strip()] = v
+    if "P0" not in P or "P1" not in P:
+        raise ValueError(f"{path}: P0/P1 not found")
+    return _resize_projection([P["P0"], P["P1"]], (1241, 376), do_resize)
+
+
+def load_projection_opencv_yml(path_left, path_right, do_resize=True):
+    """OpenCV FileStorage YAML per camera (StereoCameraModel.cpp:32-68): `image_width`, `image_height` (left file) and
+    `projection_matrix: !!opencv-matrix {rows: 3, cols: 4, dt: d, data: [...]}`.  -> (P_l, P_r)."""
+    import re
+    size, P = [0, 0], []
+    for lr, path in enumerate((path_left, path_right)):
+        txt = open(path).read()
+        if lr == 0:
+            for i, key in enumerate(("image_width", "image_height")):
+                m = re.search(rf"^{key}\s*:\s*(\d+)", txt, re.M)
+                if m:
+                    size[i] = int(m.group(1))
+        m = re.search(r"projection_matrix\s*:.*?rows\s*:\s*(\d+).*?cols\s*:\s*(\d+).*?data\s*:\s*\[(.*?)\]", txt, re.S)
+        if not m:
+            raise ValueError(f"{path}: projection_matrix not found")
+        if (int(m.group(1)), int(m.group(2))) != (3, 4):
+            raise ValueError(f"{path}: illegal projection matrix size ({m.group(1)},{m.group(2)})")
+        P.append([float(t) for t in m.group(3).replace("\n", " ").split(",")])
+    if do_resize and (size[0] <= 0 or size[1] <= 0):
+        raise ValueError("image_width / image_height missing: cannot resize")
+    return _resize_projection(P, size, do_resize)
