@@ -17,14 +17,17 @@ namespace u96 {
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 
-// v = a + 2b + c for 4 bytes -> two u16x2 registers (px0,px1) (px2,px3)
-__device__ __forceinline__ void vsum4(uint32_t a, uint32_t b, uint32_t c, uint32_t &lo, uint32_t &hi)
+// 16 pixels of a row widened to eight u16x2 registers (px0,px1) ... (px14,px15): every input row is widened once and
+// then serves three output rows (the vertical 1-2-1 sums are plain 32-bit adds: at most 4*255 per half, no carry)
+struct WideRow { uint32_t v[8]; };
+__device__ __forceinline__ WideRow widen16(const uint4 r)
 {
-    const uint32_t al = prmt(a, 0, 0x4140), ah = prmt(a, 0, 0x4342);
-    const uint32_t bl = prmt(b, 0, 0x4140), bh = prmt(b, 0, 0x4342);
-    const uint32_t cl = prmt(c, 0, 0x4140), ch = prmt(c, 0, 0x4342);
-    lo = al + 2u * bl + cl;       // max 4*255 = 1020 per half: no carry between halves
-    hi = ah + 2u * bh + ch;
+    WideRow w;
+    w.v[0] = prmt(r.x, 0, 0x4140); w.v[1] = prmt(r.x, 0, 0x4342);
+    w.v[2] = prmt(r.y, 0, 0x4140); w.v[3] = prmt(r.y, 0, 0x4342);
+    w.v[4] = prmt(r.z, 0, 0x4140); w.v[5] = prmt(r.z, 0, 0x4342);
+    w.v[6] = prmt(r.w, 0, 0x4140); w.v[7] = prmt(r.w, 0, 0x4342);
+    return w;
 }
 
 // One thread = 16 pixels x XS_R consecutive rows: the XS_R+2 input rows are all requested before any
@@ -68,23 +71,22 @@ __global__ void __launch_bounds__(256) k_xsobel(const uint8_t *__restrict__ srcL
         row[j] = *reinterpret_cast<const uint4 *>(p);
         nl[j] = p[xl]; nr[j] = p[xr];
     }
+    WideRow wa = widen16(row[0]), wb = widen16(row[1]);
 #pragma unroll
     for (int i = 0; i < XS_R; i++) {
         const int y = y0 + i;
         if (y >= H) break;
+        const WideRow wc = widen16(row[i + 2]);
         uint4 o4;
         if (PROFILE == U96_PROFILE_RTL && (y == 0 || y == H - 1)) o4 = make_uint4(0, 0, 0, 0);       // invalid lines
         else if (PROFILE == U96_PROFILE_OPENCV && (H & 1) && y == H - 1) {
             const uint32_t c4 = (uint32_t)cap * 0x01010101u;
             o4 = make_uint4(c4, c4, c4, c4);
         } else {
-            const uint4 a = row[i], b = row[i + 1], c = row[i + 2];
             uint32_t v[10];      // v[0] = (-, px-1) ; v[1..8] = pairs (px0,px1)...(px14,px15) ; v[9] = (px16, -)
             v[0] = (nl[i] + 2u * nl[i + 1] + nl[i + 2]) << 16;
-            vsum4(a.x, b.x, c.x, v[1], v[2]);
-            vsum4(a.y, b.y, c.y, v[3], v[4]);
-            vsum4(a.z, b.z, c.z, v[5], v[6]);
-            vsum4(a.w, b.w, c.w, v[7], v[8]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[1 + k] = wa.v[k] + 2u * wb.v[k] + wc.v[k];
             v[9] = nr[i] + 2u * nr[i + 1] + nr[i + 2];
             uint32_t o[4];
 #pragma unroll
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) k_xsobel(const uint8_t *__restrict__ srcL
             o4 = make_uint4(o[0], o[1], o[2], o[3]);
         }
         *reinterpret_cast<uint4 *>(dst + (size_t)i * dp) = o4;
+        wa = wb; wb = wc;
     }
 }
 
