@@ -41,6 +41,17 @@ def shard_frames(total, rank, world):
     return list(range(rank, total, world))
 
 
+def gather_disparity(t, rank, world, dst=0):
+    """The optional exchange step of SURVEY 8(e): every rank's disparity maps (same shape on all ranks) collected on rank
+    `dst` -- NCCL send/recv over NVLink on the GPUs, gloo on CPU tensors in the tests.  Returns the list on dst, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    tb = t.contiguous().view(torch.uint8)            # int16 is not a collective dtype (NCCL, gloo): ship the bytes
+    out = [torch.empty_like(tb) for _ in range(world)] if rank == dst else None
+    dist.gather(tb, out, dst=dst)
+    return [o.view(t.dtype) for o in out] if out is not None else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -175,6 +186,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="N>1: also time the optional gather of all disparity maps onto rank 0")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -269,6 +281,27 @@ def main():
     fps = frames_total / (ms_total_max * 1e-3)
     for k in stage:
         stage[k] /= args.steps
+    gather = None
+    if args.gather and world > 1:
+        # optional, off the hot path: the step's disparity maps of every rank onto rank 0 over NVLink (zero-copy send buffer)
+        t_d = fe.disp_tensor((args.steps - 1) & 1)
+        for _ in range(3):                             # the first send/recv pairs connect the P2P channels lazily
+            gather_disparity(t_d, rank, world)
+        torch.cuda.synchronize(); dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(5):
+            got = gather_disparity(t_d, rank, world)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1) / 5], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ok = all(torch.equal(got[0], t_d) for _ in (0,)) and len(got) == world
+            nbytes = t_d.numel() * 2
+            gather = {"ms": float(tg.item()), "bytes_per_rank": nbytes, "gbs_into_rank0": (world - 1) * nbytes / float(tg.item()) / 1e6,
+                      "frames_per_s_incl_gather": frames_total / ((ms_total_max + args.steps * float(tg.item())) * 1e-3), "ok": bool(ok)}
+        del t_d
     fe.close()
     del dL, dR
 
@@ -394,6 +427,8 @@ def main():
                         "pcie": pcie},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "single_pair_latency": latency}
+        if gather is not None:
+            line["gather"] = gather
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -81,7 +81,7 @@ GLOO_WORKER = r"""
 import os, sys, json
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
-from bench import shard_frames
+from bench import shard_frames, gather_disparity
 import u96_slam_b200 as u
 from oracle_py import Oracle
 dist.init_process_group("gloo")
@@ -90,17 +90,27 @@ o = Oracle()
 mine = shard_frames(6, rank, world)
 # each rank works on its own frames only (no data-path collective); the checksum of checksums is gathered
 cs = 0
+maps = []
 for i in mine:
     L, R = u.synth_pair(1, i, 160, 96, 32)
     d = o.bm_rtl(o.xsobel_rtl(L), o.xsobel_rtl(R), wsz=9, ndisp=32)
     cs += int(d.astype(np.int64).sum())
+    maps.append(d)
+# the optional exchange step (SURVEY 8e): all disparity maps onto rank 0, re-interleaved into stream order
+got = gather_disparity(torch.from_numpy(np.stack(maps)), rank, world)
+gsum = -1
+if rank == 0:
+    full = np.empty((6,) + maps[0].shape, np.int16)
+    for r in range(world):
+        full[shard_frames(6, r, world)] = got[r].numpy()
+    gsum = int(full.astype(np.int64).sum()) + int(full[5].astype(np.int64).sum())      # order-sensitive: frame 5 counted twice
 t = torch.tensor([cs, len(mine)], dtype=torch.int64)
 dist.barrier()
 dist.all_reduce(t)
 ms = torch.tensor([1.0 + rank], dtype=torch.float64)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)           # bench.py: max-over-ranks time
 if rank == 0:
-    print(json.dumps({"sum": int(t[0]), "frames": int(t[1]), "max_ms": float(ms[0])}))
+    print(json.dumps({"sum": int(t[0]), "frames": int(t[1]), "max_ms": float(ms[0]), "gathered": gsum}))
 dist.destroy_process_group()
 """
 
@@ -117,11 +127,12 @@ def test_frame_sharding_world_size_2_gloo(tmp_path, oracle):
                          capture_output=True, text=True, env=env, timeout=280)
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
-    want = 0
+    want, last = 0, 0
     for i in range(6):
         L, R = u.synth_pair(1, i, 160, 96, 32)
-        want += int(oracle.bm_rtl(oracle.xsobel_rtl(L), oracle.xsobel_rtl(R), wsz=9, ndisp=32).astype(np.int64).sum())
-    assert res == {"sum": want, "frames": 6, "max_ms": 2.0}
+        last = int(oracle.bm_rtl(oracle.xsobel_rtl(L), oracle.xsobel_rtl(R), wsz=9, ndisp=32).astype(np.int64).sum())
+        want += last
+    assert res == {"sum": want, "frames": 6, "max_ms": 2.0, "gathered": want + last}
 
 
 def test_bench_reference_arm_prints_contract_line():

@@ -280,6 +280,18 @@ class StereoFrontEnd:
                "u96_bank_device_ptr")
         return p.value, pitch.value, frame.value
 
+    def disp_tensor(self, bank):
+        """Zero-copy torch view (n, H, W) int16 of the bank's disparity maps in HBM (u96_bank_device_ptr), e.g. as the
+        send buffer of the optional multi-GPU gather; valid until the bank is submitted again."""
+        import torch
+        ptr, pitch, frame = self.bank_device_ptr(bank, BUF_DISP)
+        n = self._n[bank]
+
+        class _Cai:                                    # CUDA array interface v2
+            __cuda_array_interface__ = {"shape": (n, self.H, self.W), "typestr": "<i2", "data": (ptr, False), "version": 2,
+                                        "strides": (frame, pitch, 2)}
+        return torch.as_tensor(_Cai(), device=f"cuda:{self.device}")
+
     def last_stage_ms(self, bank):
         ms = (ctypes.c_float * 4)()
         _check(self.L, self.L.u96_last_stage_ms(self.h, bank, ms), "u96_last_stage_ms")
