@@ -524,3 +524,21 @@ def test_randomised_shapes_and_parameters_both_profiles(u, oracle):
                     want = oracle.bm_cv(oracle.xsobel_cv(L[k], cap), oracle.xsobel_cv(R[k], cap), wsz=B, ndisp=D, prefilter_cap=cap,
                                         texture_threshold=tex, uniqueness_ratio=uq)
                     assert np.array_equal(d[k], want), ("cv", W, H, D, B, cap, tex, uq, int((d[k] != want).sum()))
+
+
+def test_zero_copy_disparity_view(u, fe640, golden):
+    """StereoFrontEnd.disp_tensor: a torch view of the DISP bank in HBM (the send buffer of the optional multi-GPU gather)
+    holds exactly what u96_receive_disp copies out, also for a pitch wider than the image."""
+    import torch
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    fe640.submit_rect(0, np.stack([golden["rect_l"]] * 2), np.stack([golden["rect_r"]] * 2)); b = fe640.wait()
+    t = fe640.disp_tensor(b)
+    assert t.is_cuda and t.dtype == torch.int16 and tuple(t.shape) == (2, 480, 640)
+    assert np.array_equal(t.cpu().numpy(), fe640.receive_disp(b))
+    W, H = 650, 40                                               # pitch 768 > W: strided view
+    L, R = u.synth_batch(4, 0, 2, W, H, 64)
+    with u.StereoFrontEnd(0, W, H, 2) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=9, num_disparities=64, x_store_offset=1)
+        fe.submit_rect(0, L, R); b = fe.wait()
+        t = fe.disp_tensor(b)
+        assert not t.is_contiguous() and np.array_equal(t.contiguous().cpu().numpy(), fe.receive_disp(b))
