@@ -72,17 +72,29 @@ int launch_rect_build_map(const RectMapParams &rp, int2 *map, cudaStream_t s)
 // Word path (taken when the source columns of the 4 pixels span <= 6 bytes and their source rows span <= 2 rows,
 // i.e. almost everywhere for a rectifying rotation): the 2 or 3 source rows are fetched as 3 aligned 32-bit
 // words each and funnel-shifted into 8 consecutive bytes; the taps are byte-permuted out and interpolated as
-//   64*s + 2^15 = sum_rows (64*wy_row) * dp4a({left,right},{32-xf,xf}) + 2^15
-// which equals the RTL's sum of four u1.10-weighted taps (rect_intp.v:337-378) by distributivity; the
-// rounding ((s>>9)+1)>>1 == (s+512)>>10 (the 0xFF clamp of rect_intp.v:399-405 is unreachable: s <= 255*1024),
-// so the result is byte 2 of the accumulator and four pixels are packed with three PRMTs.
+//   64*s + 2^15 = sum_rows dp2a({64*wy_row*(32-xf), 64*wy_row*xf}, {left, right}) + 2^15
+// i.e. the RTL's sum of four u1.10-weighted taps (rect_intp.v:337-378) scaled by 64, one IDP.2A (16-bit weights x 8-bit
+// taps) per source row; the rounding ((s>>9)+1)>>1 == (s+512)>>10 (the 0xFF clamp of rect_intp.v:399-405 is
+// unreachable: s <= 255*1024), so the result is byte 2 of the accumulator and four pixels are packed with three PRMTs.
+// The only weight that does not fit 16 bits is 64*1024 (xf = yf = 0, all other weights zero); it is stored as 65535,
+// which still yields (tap*65535 + 2^15) >> 16 == tap.
 // ROWS = 2 when no lane of the warp straddles a source-row step, else 3 (warp-uniform choice, no divergence).
 constexpr int RECT_FPB = 8;
 
+// packed 16-bit weight pairs {left | right << 16} of one pixel for the up to three source rows of its group, scaled by 64
+__device__ __forceinline__ void row_weights(uint32_t (&wr)[3], int xf, int yf, bool up)
+{
+    const uint32_t a = 64u * (uint32_t)(32 - yf), b = 64u * (uint32_t)yf;
+    const uint32_t w0 = up ? a : 0u, w1 = up ? b : a, w2 = up ? 0u : b;
+    const uint32_t xl = (uint32_t)(32 - xf), xr = (uint32_t)xf;
+    wr[0] = min(w0 * xl, 65535u) | ((w0 * xr) << 16);
+    wr[1] = min(w1 * xl, 65535u) | ((w1 * xr) << 16);
+    wr[2] = min(w2 * xl, 65535u) | ((w2 * xr) << 16);
+}
+
 template <int ROWS>
 __device__ __forceinline__ void remap_words(const uint32_t *__restrict__ w, uint8_t *__restrict__ dst, int spw, size_t sfw, size_t df,
-                                            int nf, int mis, const uint32_t (&selw)[4], const uint32_t (&wx)[4],
-                                            const uint32_t (&wy)[4][3])
+                                            int nf, int mis, const uint32_t (&selw)[4], const uint32_t (&wr)[4][3])
 {
 #pragma unroll 4
     for (int f = 0; f < nf; f++) {
@@ -98,7 +110,7 @@ __device__ __forceinline__ void remap_words(const uint32_t *__restrict__ w, uint
         for (int k = 0; k < 4; k++) {
             acc[k] = 1u << 15;
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) acc[k] += __dp4a(__byte_perm(lo[r], hi[r], selw[k]), wx[k], 0u) * wy[k][r];
+            for (int r = 0; r < ROWS; r++) acc[k] = __dp2a_lo(wr[k][r], __byte_perm(lo[r], hi[r], selw[k]), acc[k]);
         }
         const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
         *reinterpret_cast<uint32_t *>(dst) = __byte_perm(p01, p23, 0x5410);      // pitch is a multiple of 128: always in-row
@@ -144,22 +156,19 @@ __global__ void __launch_bounds__(128, 8) k_rect_remap(const uint8_t *__restrict
     if (words) {
         const int o0 = ymin * sp + xi[0];
         const int mis = (o0 & 3) * 8;
-        uint32_t selw[4], wx[4], wy[4][3];
+        uint32_t selw[4], wr[4][3];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t dk = (uint32_t)(xi[k] - xi[0]);
-            selw[k] = dk | ((dk + 1) << 4);                           // bytes dk, dk+1 ; the upper two bytes meet zero weights
-            wx[k] = (uint32_t)(32 - xf[k]) | ((uint32_t)xf[k] << 8);  // u8 weights for dp4a
-            const uint32_t a = 64u * (uint32_t)(32 - yf[k]), b = 64u * (uint32_t)yf[k];
-            const bool up = (yi[k] == ymin);
-            wy[k][0] = up ? a : 0u; wy[k][1] = up ? b : a; wy[k][2] = up ? 0u : b;
+            selw[k] = dk | ((dk + 1) << 4);                           // bytes dk, dk+1 ; dp2a.lo ignores the upper two bytes
+            row_weights(wr[k], xf[k], yf[k], yi[k] == ymin);
         }
         const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (o0 >> 2);
         // the third row is only touched when some lane of the warp needs it; lanes at the bottom edge clamp it
         if (any3) {
-            if (ymin + 2 < H) remap_words<3>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wx, wy);
-            else              remap_words<2>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wx, wy);
-        } else remap_words<2>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wx, wy);
+            if (ymin + 2 < H) remap_words<3>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wr);
+            else              remap_words<2>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wr);
+        } else remap_words<2>(w, dst, sp >> 2, sf >> 2, df, nf, mis, selw, wr);
         return;
     }
 
@@ -248,7 +257,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, in
 // words of one 4-pixel group out of the shared-memory box (same arithmetic as remap_words)
 template <int ROWS>
 __device__ __forceinline__ uint32_t remap_group_smem(const uint32_t *w, int bww, uint32_t mis, const uint32_t (&selw)[4],
-                                                     const uint32_t (&wx)[4], const uint32_t (&wy)[4][3])
+                                                     const uint32_t (&wr)[4][3])
 {
     uint32_t lo[ROWS], hi[ROWS];
 #pragma unroll
@@ -262,7 +271,7 @@ __device__ __forceinline__ uint32_t remap_group_smem(const uint32_t *w, int bww,
     for (int k = 0; k < 4; k++) {
         acc[k] = 1u << 15;
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) acc[k] += __dp4a(__byte_perm(lo[r], hi[r], selw[k]), wx[k], 0u) * wy[k][r];
+            for (int r = 0; r < ROWS; r++) acc[k] = __dp2a_lo(wr[k][r], __byte_perm(lo[r], hi[r], selw[k]), acc[k]);
     }
     const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
     return __byte_perm(p01, p23, 0x5410);
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rect_remap_tma(const __grid_cons
     const int bww = BW >> 2;
     int mode[RT_G];                    // 0 dead, 2/3 word path with that many rows, 1 generic
     int o0[RT_G];
-    uint32_t mis[RT_G], selw[RT_G][4], wx[RT_G][4], wy[RT_G][4][3];
+    uint32_t mis[RT_G], selw[RT_G][4], wr[RT_G][4][3];
     size_t doff[RT_G];
 #pragma unroll
     for (int g = 0; g < RT_G; g++) {
@@ -337,10 +346,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rect_remap_tma(const __grid_cons
         for (int k = 0; k < 4; k++) {
             const uint32_t dk = (uint32_t)(xi[k] - xi[0]) & 7u;
             selw[g][k] = dk | ((dk + 1) << 4);
-            wx[g][k] = (uint32_t)(32 - xf[k]) | ((uint32_t)xf[k] << 8);
-            const uint32_t a = 64u * (uint32_t)(32 - yf[k]), b = 64u * (uint32_t)yf[k];
-            const bool up = (yi[k] == ymin);
-            wy[g][k][0] = up ? a : 0u; wy[g][k][1] = up ? b : a; wy[g][k][2] = up ? 0u : b;
+            row_weights(wr[g][k], xf[k], yf[k], yi[k] == ymin);
         }
     }
     uint8_t *dbase = (cam ? dR : dL) + (size_t)f0 * df;
@@ -354,8 +360,8 @@ __global__ void __launch_bounds__(RT_THREADS) k_rect_remap_tma(const __grid_cons
             out[g] = 0;
             if (mode[g] >= 2) {
                 const uint32_t *w = reinterpret_cast<const uint32_t *>(sb) + (o0[g] >> 2);
-                out[g] = (mode[g] == 3) ? remap_group_smem<3>(w, bww, mis[g], selw[g], wx[g], wy[g])
-                                        : remap_group_smem<2>(w, bww, mis[g], selw[g], wx[g], wy[g]);
+                out[g] = (mode[g] == 3) ? remap_group_smem<3>(w, bww, mis[g], selw[g], wr[g])
+                                        : remap_group_smem<2>(w, bww, mis[g], selw[g], wr[g]);
             } else if (mode[g] == 1) {
                 // generic path (exotic maps): byte gathers; every tap lies inside the box, outside-image taps are TMA zero fill
                 const int y = ty0 + warp + 8 * g;
