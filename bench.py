@@ -36,6 +36,30 @@ WORKLOADS = {
 }
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads to the NUMA node its GPU hangs off, BEFORE the pinned staging buffers are allocated
+    (first touch then places them on that node), so that N ranks do not all stream through one memory controller.
+    Returns the node, or None when the topology is not exposed (VMs often report -1)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_frames(total, rank, world):
     """Frame indices of `rank` when `total` frames are dealt round-robin over `world` GPUs."""
     return list(range(rank, total, world))
@@ -206,6 +230,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -424,7 +449,7 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(2 * W * H * nb),
                         "d2h_bytes_per_step": int(2 * W * H * nb), "steps": e2e_steps, "checksum": checksum,
                         "timing": "wall clock around u96_submit_raw_async/u96_wait over two banks, synchronize on both sides",
-                        "pcie": pcie},
+                        "pcie": pcie, "host_numa_node_rank0": numa_node},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "single_pair_latency": latency}
         if gather is not None:
