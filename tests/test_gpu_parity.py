@@ -299,6 +299,42 @@ def test_pipelined_async_submit_matches(u, oracle):
             assert np.array_equal(e[i], we) and int(m[i]) == wm, i
 
 
+def test_staged_host_transfers_of_unaligned_width(u, oracle):
+    """Width that is not a multiple of the internal pitch (KITTI-like 330 px here): host transfers take the tight device
+    staging area (one contiguous PCIe copy + on-device pitch conversion) in the plain, the chunk-pipelined and the receive
+    paths; every one must deliver the same bits as the oracle."""
+    import torch
+    W, H, D, B = 330, 96, 64, 9
+    L, R = u.synth_batch(7, 0, 4, W, H, D)
+    rp = u.identity_rect_params(W, H, float(W))
+    n = 70                                                       # >= 64 frames: the chunk pipeline is taken
+    reps = (n + 3) // 4
+    hL = torch.from_numpy(np.concatenate([L] * reps)[:n]).pin_memory(); hR = torch.from_numpy(np.concatenate([R] * reps)[:n]).pin_memory()
+    out = torch.empty((n, H, W), dtype=torch.int16).pin_memory()
+    with u.StereoFrontEnd(0, W, H, n) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=B, num_disparities=D, x_store_offset=1)
+        fe.set_rect_params(rp)
+        fe.submit_host_ptr_async("raw", 0, hL.data_ptr(), hR.data_ptr(), W, n, out.data_ptr())
+        assert fe.wait() == 0
+        assert np.array_equal(out.numpy(), fe.receive_disp(0))   # staged D2H of the pipeline == staged D2H of receive
+        rl_all, rr_all = fe.receive_rect(0)
+        xl_all, xr_all = fe.receive_xsbl(0)
+        for i in (0, 1, 2, 3, 63, 64, 69):
+            j = i % 4
+            rl, rr = oracle.rectify(L[j], rp, 0), oracle.rectify(R[j], rp, 1)
+            assert np.array_equal(rl_all[i], rl) and np.array_equal(rr_all[i], rr), i
+            xl, xr = oracle.xsobel_rtl(rl), oracle.xsobel_rtl(rr)
+            assert np.array_equal(xl_all[i], xl) and np.array_equal(xr_all[i], xr), i
+            assert np.array_equal(out[i].numpy(), oracle.bm_rtl(xl, xr, wsz=B, ndisp=D)), i
+        # plain (non-pipelined) path: a short batch from pageable memory
+        fe.submit_raw(1, L[:3], R[:3])
+        assert fe.wait() == 1
+        d = fe.receive_disp(1)
+        for j in range(3):
+            rl, rr = oracle.rectify(L[j], rp, 0), oracle.rectify(R[j], rp, 1)
+            assert np.array_equal(d[j], oracle.bm_rtl(oracle.xsobel_rtl(rl), oracle.xsobel_rtl(rr), wsz=B, ndisp=D)), j
+
+
 def test_c5_slam_loop_octomap(u, oracle, tmp_path):
     """BASELINE config C5: BM disparity -> x4 decimation -> reprojectTo3D -> pose -> OctoMap (main.cpp:495-561) through
     host/slam_loop (C++ shim + the reference's vendored OctoMap), point set checked against the oracle."""
