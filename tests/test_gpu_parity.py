@@ -335,6 +335,26 @@ def test_staged_host_transfers_of_unaligned_width(u, oracle):
             assert np.array_equal(d[j], oracle.bm_rtl(oracle.xsobel_rtl(rl), oracle.xsobel_rtl(rr), wsz=B, ndisp=D)), j
 
 
+@pytest.mark.parametrize("W,B", [(361, 25), (360, 25), (360, 27)])
+def test_bm_window_blocks_at_the_tile_edge(u, oracle, W, B):
+    """wsz 25 / 27 on the 5-warp tile with 134-136 centres in the last tile: the window sum of the last valid segment is built
+    from whole blocks that cover one column past the tile (subtracted again by the fix-up).  Regression test for the
+    racecheck finding (pad columns behind the column-sum buffers); repeated launches, bit-exact every time."""
+    H, D = 72, 64
+    L, R = u.synth_batch(11, 0, 2, W, H, D)
+    with u.StereoFrontEnd(0, W, H, 8) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=B, num_disparities=D, x_store_offset=1)
+        xl = np.stack([oracle.xsobel_rtl(L[0]), oracle.xsobel_rtl(L[1])] * 4)
+        xr = np.stack([oracle.xsobel_rtl(R[0]), oracle.xsobel_rtl(R[1])] * 4)
+        want = [oracle.bm_rtl(xl[j], xr[j], wsz=B, ndisp=D) for j in range(2)]
+        for rep in range(6):
+            fe.submit_xsbl(rep & 1, xl, xr)
+            assert fe.wait() == (rep & 1)
+            d = fe.receive_disp(rep & 1)
+            for i in range(8):
+                assert np.array_equal(d[i], want[i & 1]), (rep, i)
+
+
 def test_c5_slam_loop_octomap(u, oracle, tmp_path):
     """BASELINE config C5: BM disparity -> x4 decimation -> reprojectTo3D -> pose -> OctoMap (main.cpp:495-561) through
     host/slam_loop (C++ shim + the reference's vendored OctoMap), point set checked against the oracle."""
