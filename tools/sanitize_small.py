@@ -10,8 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import u96_slam_b200 as u  # noqa: E402
 
-for (W, H, D, B, prof, uni) in ((640, 96, 64, 21, 0, 0), (640, 96, 64, 21, 0, 1), (640, 96, 64, 15, 1, 0), (330, 80, 128, 9, 0, 0),
-                                (330, 80, 128, 9, 1, 0), (530, 70, 256, 21, 0, 0), (530, 70, 256, 11, 1, 0), (200, 64, 96, 7, 0, 0)):
+CONFIGS = ((640, 96, 64, 21, 0, 0), (640, 96, 64, 21, 0, 1), (640, 96, 64, 15, 1, 0), (330, 80, 128, 9, 0, 0),
+                                (330, 80, 128, 9, 1, 0), (530, 70, 256, 21, 0, 0), (530, 70, 256, 11, 1, 0), (200, 64, 96, 7, 0, 0))
+rot = int(sys.argv[1]) if len(sys.argv) > 1 else 0                     # start with another configuration (first-launch effects)
+for (W, H, D, B, prof, uni) in CONFIGS[rot:] + CONFIGS[:rot]:
     n = 3
     L, R = u.synth_batch(5, 0, n, W, H, D)
     with u.StereoFrontEnd(0, W, H, n) as fe:
