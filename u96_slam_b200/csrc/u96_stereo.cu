@@ -177,6 +177,12 @@ int u96_create(u96_handle **out, int device, int max_w, int max_h, int max_batch
                 cudaMalloc(&k.xsbl[i], img) != cudaSuccess) return fail(U96_ERR_NOMEM);
         }
         if (cudaMalloc(&k.disp, img * sizeof(int16_t)) != cudaSuccess) return fail(U96_ERR_NOMEM);
+        // the banks start zeroed (like the firmware's memset of the DDR banks, fpga.c:105-114): the vectorised loads of the
+        // kernels touch the pitch padding right of the image, which no kernel ever writes
+        for (int i = 0; i < 2; i++)
+            if (cudaMemset(k.raw[i], 0, img) != cudaSuccess || cudaMemset(k.rect[i], 0, img) != cudaSuccess ||
+                cudaMemset(k.xsbl[i], 0, img) != cudaSuccess) return fail(U96_ERR_CUDA);
+        if (cudaMemset(k.disp, 0, img * sizeof(int16_t)) != cudaSuccess) return fail(U96_ERR_CUDA);
         if (cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking) != cudaSuccess) return fail(U96_ERR_CUDA);
         if (cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming) != cudaSuccess) return fail(U96_ERR_CUDA);
         for (int i = 0; i < 3; i++)
