@@ -145,6 +145,18 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
 
 
+def test_bench_fails_loudly_without_a_gpu_and_numa_binding_is_optional():
+    """bench.py's product arm has no CPU fallback; the rank-to-NUMA binding degrades to None when the topology is not exposed."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import torch
+    if not torch.cuda.is_available():
+        assert bench.bind_to_gpu_numa_node(0) is None        # no CUDA device: nothing to bind to, and no exception
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                             capture_output=True, text=True, timeout=280)
+        assert out.returncode != 0 and out.stdout.strip() == "" and "no CPU fallback" in out.stderr
+
+
 def test_projection_matrix_loaders(tmp_path):
     """KITTI calib.txt and OpenCV-yml projection matrices (StereoCameraModel.cpp:19-122), incl. the 640x480 rescale."""
     import u96_slam_b200 as u
