@@ -13,6 +13,10 @@
  *   - every function returns 0 or a negative U96_ERR_* code; the library
  *     never exits and never spins.
  *   - there is no CPU fallback: without a CUDA device u96_create fails.
+ *   - like the FPGA's register file, the configuration (u96_set_bm_params, u96_set_bm_registers,
+ *     u96_set_rect_params, u96_set_stream) may only change while no bank is in flight: the setters return
+ *     U96_ERR_STATE between a submit and the u96_wait() that reports its bank.  A bank remembers the geometry
+ *     it was filled with; receive_* / reproject / uvc use that, not the current configuration.
  *
  * A "batch" is n stereo pairs stored back to back (frame i of an image starts
  * at base + i*stride*height).
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define U96_ABI_VERSION 4
+#define U96_ABI_VERSION 5
 
 enum {
     U96_OK = 0,
@@ -111,10 +115,22 @@ int  u96_submit_xsbl(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R
  * overlap on internal streams.  u96_wait() for the bank covers the copies.  disp_out may be NULL. */
 int  u96_submit_raw_async (u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n, int16_t *disp_out);
 int  u96_submit_rect_async(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n, int16_t *disp_out);
-/* same three entry points for inputs already resident in device memory (no copy) */
+/* same three entry points for inputs already resident in device memory.  16-byte aligned pointers with a stride that is
+ * a multiple of 16 and >= width rounded up to 16 are used IN PLACE (no copy; the kernels' vector loads read the row padding
+ * up to that rounded width, never write it): the caller's buffers must then stay valid and unchanged until the bank is
+ * submitted again -- u96_receive_rect / u96_receive_xsbl / u96_receive_uvc of that bank read them after u96_wait().
+ * Other pointers / strides are copied into the bank (device to device). */
 int  u96_submit_raw_device (u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n);
 int  u96_submit_rect_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n);
 int  u96_submit_xsbl_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n);
+
+/* Fpga::setRectImage alone (FPGA.cpp:236-249): the n rectified pairs are written into the RECT bank and nothing runs;
+ * returns when the caller's buffers may be reused (the reference's memcpy).  u96_receive_rect of the bank then reads
+ * them back like Fpga::receiveRectImages would. */
+int  u96_set_rect_image(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n);
+/* reg->xsbl.Control |= FPGA_XSBL_SW_START (main.cpp:172-174, FPGA.h:289): x-Sobel -> BM on what the
+ * RECT bank holds (filled by u96_set_rect_image); completion is reported by u96_wait like for a submit. */
+int  u96_start_xsbl(u96_handle *h, int bank);
 
 /* Fpga::waitIpcMessage(IPC_MSG2_DATA_READY) + IpcParameter2 (FPGA.cpp:217-220, 310-314):
  * blocks until the oldest submitted bank is complete and returns its index. */
@@ -135,6 +151,20 @@ int  u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp);
  * flags bit0: apply StereoCameraModel localTransform (StereoCameraModel.cpp:9-14). */
 int  u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_r[12],
                    int decim, int flags, float *xyz);
+/* The same dense consumer with the transforms of main.cpp:535-541 spelled out: every finite point goes through
+ * transformPoint (Stereo.cpp:189-198) with local_T (3x4 row-major floats; NULL or all zero = none, Transform::isNull)
+ * and then with the frame's pose (poses = n x 12 floats, host; NULL = none).  Points the reference skips are NaN. */
+int  u96_reproject_ex(u96_handle *h, int bank, const double P_l[12], const double P_r[12], int decim,
+                      const float *local_T, const float *poses, float *xyz);
+/* generateKeypoints3DStereo (Stereo.cpp:53-117) as the real-time loop calls it every frame through generateKeypoints3D
+ * (Stereo.cpp:119-154, main.cpp:250-252) with a dense-map depth method: for each of the n keypoints uv[i] = (x, y) of frame
+ * `frame` of the bank: disparity = map[(int)y][(int)x] / 16.0f, negative -> 0, 0 -> bad point; projectDisparityTo3D with the
+ * FLOAT keypoint coordinates; kept iff finite and (min_depth < 0 or z > min_depth) and (max_depth <= 0 or z <= max_depth);
+ * then local_T as above.  mask: n bytes (0 = skip) or NULL.  xyz: n x 3 floats, NaN = bad point.  Keypoints outside the
+ * map (undefined behaviour in the reference) are bad points.  generateKeypoints3D passes min_depth = max_depth = 0. */
+int  u96_reproject_points(u96_handle *h, int bank, int frame, const double P_l[12], const double P_r[12],
+                          const float *uv, int n, const uint8_t *mask, float min_depth, float max_depth,
+                          const float *local_T, float *xyz);
 
 /* Fpga::receiveEigen (FPGA.cpp:281-296): CV_16UC1 min-eigenvalue map (n*H*W u16, rows 0,1,H-2,H-1 zero like the
  * firmware-cleared GFTT bank) and the per-frame maximum the FPGA latches in gftt.Max (gftt_obuf.v:90-118); max_eig
@@ -154,11 +184,19 @@ int  u96_bank_device_ptr(u96_handle *h, int bank, int which, void **dptr, int *p
 /* ---- auxiliaries ----------------------------------------------------------------------- */
 /* pinned host staging memory for full-rate H2D/D2H */
 int  u96_host_alloc(void **p, size_t bytes);
+/* write-combined pinned memory: for INPUT staging buffers the host only writes sequentially (reads are very slow) */
+int  u96_host_alloc_wc(void **p, size_t bytes);
 int  u96_host_free(void *p);
 /* Perf-style stage timers (slam/include/core/Perf.h): ms of the last completed submit
- * [0]=h2d [1]=rect [2]=xsbl [3]=bm ; needs u96_set_profiling(h,1) */
+ * [0]=h2d [1]=rect(+gftt) [2]=xsbl [3]=bm(+post filters) ; needs u96_set_profiling(h,1) */
 int  u96_set_profiling(u96_handle *h, int on);
 int  u96_last_stage_ms(u96_handle *h, int bank, float ms[4]);
+/* every stage of the last completed (non-pipelined) submit of a bank on its own: ms[U96_STAGE_*], count <= U96_STAGE_COUNT */
+enum { U96_STAGE_H2D = 0, U96_STAGE_RECT, U96_STAGE_GFTT, U96_STAGE_XSBL, U96_STAGE_BM, U96_STAGE_POST, U96_STAGE_COUNT };
+int  u96_last_stage_ms_ex(u96_handle *h, int bank, float *ms, int count);
+/* kernel time of the last u96_reproject(_ex) / u96_reproject_points / u96_receive_uvc call (profiling on) */
+enum { U96_AUX_REPROJECT = 0, U96_AUX_REPROJECT_POINTS, U96_AUX_UVC, U96_AUX_COUNT };
+int  u96_last_aux_ms(u96_handle *h, int which, float *ms);
 /* number of kernels this handle has launched so far */
 int64_t u96_kernel_launches(u96_handle *h);
 /* issue-rate micro-benchmark used for the INT roofline denominator:

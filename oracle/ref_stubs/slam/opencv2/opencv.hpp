@@ -1,0 +1,1 @@
+#include "opencv2/cvstub.hpp"

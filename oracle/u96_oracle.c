@@ -495,39 +495,102 @@ void orc_filter_speckles(int16_t *img, int W, int H, int new_val, int max_size, 
 }
 
 /* ------------------------------------------------------------------------ */
-/* reprojection: Stereo.cpp:157-182 + main.cpp:522-551 (+SensorData.cpp:50-58) */
+/* reprojection: Stereo.cpp:53-117, 157-198 + main.cpp:522-551 (+SensorData.cpp:50-58) */
 /* ------------------------------------------------------------------------ */
-void orc_reproject(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
-                   int decim, int apply_local, float *xyz)
+/* projectDisparityTo3D (Stereo.cpp:157-182) for disp > 0.  The reference mixes float and double: every store into a
+ * float variable rounds once; the volatiles pin that down under any optimisation level. */
+static void orc_project_one(float u, float v, float d, const double *P_l, const double *P_r, float *out)
 {
     const double fx_l = P_l[0], fy_l = P_l[5], cx_l = P_l[2], cy_l = P_l[6], Tx_l = P_l[3];
     const double fx_r = P_r[0], fy_r = P_r[5], cx_r = P_r[2], Tx_r = P_r[3];
+    volatile float c = (float)(cx_r - cx_l);
+    volatile float dc = d + c;                                     /* float add */
+    volatile double nx = Tx_l / fx_l - Tx_r / fx_r;
+    volatile double ny = Tx_l / fy_l - Tx_r / fy_r;
+    volatile float Wx = (float)(nx / (double)dc);
+    volatile float Wy = (float)(ny / (double)dc);
+    volatile double ax = (double)u - cx_l, ay = (double)v - cy_l;
+    out[0] = (float)(ax * (double)Wx);
+    out[1] = (float)(ay * (double)Wy);
+    out[2] = (float)(fx_l * (double)Wx);
+}
+
+/* transformPoint (Stereo.cpp:189-198): float products summed left to right, no contraction (built -ffp-contract=off) */
+static void orc_transform_point(float *p, const float *t)
+{
+    volatile float x = p[0], y = p[1], z = p[2];
+    volatile float a, b, c;
+    a = t[0] * x; b = t[1] * y; a = a + b; b = t[2] * z; a = a + b; c = a + t[3];  p[0] = c;
+    a = t[4] * x; b = t[5] * y; a = a + b; b = t[6] * z; a = a + b; c = a + t[7];  p[1] = c;
+    a = t[8] * x; b = t[9] * y; a = a + b; b = t[10] * z; a = a + b; c = a + t[11]; p[2] = c;
+}
+
+/* StereoCameraModel.cpp:9-14 */
+static const float ORC_LOCAL_T[12] = {0.0f, 0.0f, 1.0f, 0.0f, -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, -1.0f, 0.0f, 0.0f};
+
+/* Transform::isNull (Transform.cpp:88-95) */
+static int orc_transform_is_null(const float *t)
+{
+    if (!t) return 1;
+    for (int i = 0; i < 12; i++) if (t[i] != 0.0f) return 0;
+    return 1;
+}
+
+/* dense consumer (main.cpp:522-551): local_T / pose = 3x4 row-major float transforms or NULL */
+void orc_reproject_ex(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
+                      int decim, const float *local_T, const float *pose, float *xyz)
+{
     const int ow = W / decim, oh = H / decim;
     for (int row = 0; row < oh; row++) {
         for (int colx = 0; colx < ow; colx++) {
             const int16_t s = disp[(size_t)(row * decim) * W + colx * decim];
             volatile float d = (float)(s / 16.0f);                 /* main.cpp:529 */
-            float X = NAN, Y = NAN, Z = NAN;
+            float p[3] = {NAN, NAN, NAN};
             if (d > 0.0f) {
-                const float u = (float)(colx * decim), v = (float)(row * decim);
-                volatile float c = (float)(cx_r - cx_l);
-                volatile float dc = d + c;                         /* float add */
-                volatile double nx = Tx_l / fx_l - Tx_r / fx_r;
-                volatile double ny = Tx_l / fy_l - Tx_r / fy_r;
-                volatile float Wx = (float)(nx / (double)dc);
-                volatile float Wy = (float)(ny / (double)dc);
-                volatile double ax = (double)u - cx_l, ay = (double)v - cy_l;
-                X = (float)(ax * (double)Wx);
-                Y = (float)(ay * (double)Wy);
-                Z = (float)(fx_l * (double)Wx);
-                if (apply_local && isfinite(X) && isfinite(Y) && isfinite(Z)) {
-                    /* StereoCameraModel.cpp:9-14: (x,y,z) -> (z,-x,-y) */
-                    float tx = Z, ty = -X, tz = -Y;
-                    X = tx; Y = ty; Z = tz;
-                }
+                orc_project_one((float)(colx * decim), (float)(row * decim), d, P_l, P_r, p);
+                if (isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2])) {      /* main.cpp:535-538 */
+                    if (local_T) orc_transform_point(p, local_T);
+                    if (pose) orc_transform_point(p, pose);
+                } else if (local_T || pose) { p[0] = p[1] = p[2] = NAN; }      /* the consumer drops non-finite points */
             }
             float *o = xyz + ((size_t)row * ow + colx) * 3;
-            o[0] = X; o[1] = Y; o[2] = Z;
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        }
+    }
+}
+
+void orc_reproject(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
+                   int decim, int apply_local, float *xyz)
+{
+    orc_reproject_ex(disp, W, H, P_l, P_r, decim, apply_local ? ORC_LOCAL_T : NULL, NULL, xyz);
+}
+
+/* generateKeypoints3DStereo (Stereo.cpp:53-117) with a dense-map depth method: uv = n (x, y) float pairs, mask NULL or n
+ * bytes, local_T NULL (or all zero: Transform::isNull) = no transform.  A keypoint whose integer pixel lies outside the map
+ * is undefined behaviour in the reference (cv::Mat::at without a check); the build defines it as a bad point (NaN). */
+void orc_reproject_points(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
+                          const float *uv, int n, const uint8_t *mask, float min_depth, float max_depth,
+                          const float *local_T, float *xyz)
+{
+    const int have_T = !orc_transform_is_null(local_T);
+    for (int i = 0; i < n; i++) {
+        float *o = xyz + (size_t)3 * i;
+        o[0] = o[1] = o[2] = NAN;
+        if (mask && !mask[i]) continue;
+        const float x = uv[2 * i], y = uv[2 * i + 1];
+        if (!(x > -1.0f && x < (float)W && y > -1.0f && y < (float)H)) continue;   /* also rejects NaN coordinates */
+        const int xi = (int)x, yi = (int)y;                        /* truncation toward zero, :79 */
+        const int16_t s = disp[(size_t)yi * W + xi];
+        volatile float d = (float)(s / 16.0f);
+        if (d < 0) d = 0;                                          /* :81-83 */
+        if (d != 0.0f) {
+            float p[3];
+            orc_project_one(x, y, d, P_l, P_r, p);                 /* the FLOAT keypoint coordinates, :94-97 */
+            if (isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) &&
+                (min_depth < 0.0f || p[2] > min_depth) && (max_depth <= 0.0f || p[2] <= max_depth)) {
+                if (have_T) orc_transform_point(p, local_T);
+                o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+            }
         }
     }
 }

@@ -17,9 +17,13 @@
  *   - diven closed forms: pinned against a bit-serial emulation of diven.v.
  *   - cv::StereoBM profile: pinned against cv2.StereoBM 4.13 (the third-party
  *                      library the reference calls; version unpinned upstream).
- *   - BM (RTL) and reprojection: PARITY UNPINNED by reference assets (the
- *                      reference ships no disparity dump); cross-checked only
- *                      against the survey's independent numpy reading (CRCs).
+ *   - reprojection:    pinned against the reference's own Stereo.cpp /
+ *                      StereoCameraModel.cpp / Transform.cpp compiled from where
+ *                      they lie (oracle/_ref/libstereo_ref.so; OpenCV containers
+ *                      stubbed, arithmetic untouched) + tests/golden fixture.
+ *   - BM (RTL):        PARITY UNPINNED by reference assets (the reference ships
+ *                      no disparity dump); cross-checked against the survey's
+ *                      CRCs and an independent numpy reading (tests/rtl_bm_numpy.py).
  *
  * All citations are relative to /root/reference/.
  */
@@ -99,6 +103,15 @@ void orc_filter_speckles(int16_t *img, int W, int H, int new_val, int max_size, 
  * apply_local: apply StereoCameraModel.cpp:9-14 localTransform.               */
 void orc_reproject(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
                    int decim, int apply_local, float *xyz);
+/* same with explicit 3x4 row-major float transforms (NULL = skip): localTransform then the optimised pose, each through
+ * transformPoint (Stereo.cpp:189-198), exactly the dense consumer of main.cpp:522-551 */
+void orc_reproject_ex(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
+                      int decim, const float *local_T, const float *pose, float *xyz);
+/* generateKeypoints3DStereo (Stereo.cpp:53-117), dense-map depth methods: gather at (int)y,(int)x, d<0 -> 0, skip 0,
+ * projection with the float keypoint coordinates, min/max-depth gates, localTransform unless null.  NaN = bad point. */
+void orc_reproject_points(const int16_t *disp, int W, int H, const double *P_l, const double *P_r,
+                          const float *uv, int n, const uint8_t *mask, float min_depth, float max_depth,
+                          const float *local_T, float *xyz);
 
 /* UVC payload of the firmware (StereoBM/src/xusb_main.c:293-376): YUYV frame of 2W x H pixels.
  * mode 1 = USB_OUTPUT_STEREO_RECT / 2 = USB_OUTPUT_STEREO_XSBL (planar u8 L and R) / 3 = USB_OUTPUT_STEREO_BM (s16 disparity). */

@@ -16,6 +16,12 @@ Outputs
   rect_remap_ref.npz: output of the reference's own rect_remap() (fpga.c:303-366,
                       compiled from where it lies into oracle/_ref) for the
                       shipped parameter set (fpga.c:190-226).
+  reproject_ref.npz : outputs of the reference's own 3-D code (Stereo.cpp,
+                      StereoCameraModel.cpp, Transform.cpp compiled unmodified into
+                      oracle/_ref/libstereo_ref.so): the KITTI calib loader with and
+                      without the 640x480 rescale, generateKeypoints3DStereo on 2000
+                      keypoints with several depth gates, and the dense consumer
+                      (main.cpp:522-551) with localTransform and a pose.
 """
 import ctypes
 import io
@@ -51,6 +57,45 @@ def dat_digests():
     json.dump(d, open(os.path.join(HERE, "dat_sha256.json"), "w"), indent=1)
 
 
+def reproject_inputs():
+    """Deterministic inputs of the reprojection fixture (shared with the tests)."""
+    rng = np.random.default_rng(96)
+    W, H = 160, 120
+    disp = rng.integers(-40, 64 * 16, (H, W)).astype(np.int16)
+    disp[rng.random((H, W)) < 0.25] = -1                     # RTL invalid
+    disp[rng.random((H, W)) < 0.05] = -16                    # OpenCV invalid
+    disp[rng.random((H, W)) < 0.03] = 0
+    disp[0, :6] = [1, 32767, -32768, 16, 15, 0]
+    uv = np.stack([rng.random(2000) * W, rng.random(2000) * H], 1).astype(np.float32)
+    uv[:6] = [[0, 0], [W - 0.01, H - 0.01], [0.5, 0.5], [-0.5, -0.5], [5.0, 0.0], [1.75, 0.25]]
+    P_l = np.array([[718.856, 0, 607.1928, 0], [0, 718.856, 185.2157, 0], [0, 0, 1, 0]], np.float64)
+    P_r = P_l.copy(); P_r[0, 3] = -386.1448
+    pose = np.array([0.9, 0.1, -0.2, 1.5, -0.1, 0.95, 0.05, -2.25, 0.2, -0.04, 0.97, 0.3], np.float32)
+    gates = [(0.0, 0.0), (-1.0, 0.0), (2.0, 30.0), (0.0, 5.0)]
+    return W, H, disp, uv, P_l, P_r, pose, gates
+
+
+def reproject_golden():
+    import tempfile
+    from oracle_py import RefStereo
+    r = RefStereo()
+    W, H, disp, uv, P_l, P_r, pose, gates = reproject_inputs()
+    calib = os.path.join(tempfile.mkdtemp(), "calib.txt")
+    r.write_kitti_calib(calib, P_l, P_r)
+    out = {"local_transform": r.local_transform()[0]}
+    for rs in (0, 1):
+        Pl, Pr = r.model_load(calib, rs)
+        out[f"P_l_resize{rs}"] = Pl; out[f"P_r_resize{rs}"] = Pr
+        for gi, (mn, mx) in enumerate(gates):
+            out[f"kp_resize{rs}_gate{gi}"] = r.keypoints3d(calib, rs, uv, disp, mn, mx)
+        dd = np.ascontiguousarray(disp[::4, ::4][:H // 4, :W // 4])
+        out[f"dense_resize{rs}_local"] = r.dense_cloud(calib, rs, dd, 4, True, None)
+        out[f"dense_resize{rs}_local_pose"] = r.dense_cloud(calib, rs, dd, 4, True, pose)
+        if rs == 0:
+            out["dense_resize0_plain"] = r.dense_cloud(calib, rs, np.ascontiguousarray(disp), 1, False, None)
+    np.savez_compressed(os.path.join(HERE, "reproject_ref.npz"), **out)
+
+
 def main():
     import cv2
     dat_digests()
@@ -84,6 +129,7 @@ def main():
     # the reference's shipped rectifier command dump (src/dvp/sim/cmd.dat, read by the testbench sim_dvp.v:174)
     words = np.array([int(t, 16) for t in open(os.path.join(REF, "src", "dvp", "sim", "cmd.dat")).read().split()], np.uint32)
     np.savez_compressed(os.path.join(HERE, "rect_cmd_dat.npz"), words=words)
+    reproject_golden()
     print("golden fixtures written")
 
 

@@ -14,6 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 REF_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libfpga_ref.so")
+REF_STEREO_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libstereo_ref.so")
+# StereoCameraModel.cpp:9-14
+LOCAL_TRANSFORM = np.array([0, 0, 1, 0, -1, 0, 0, 0, 0, -1, 0, 0], np.float32)
 
 # shipped rectification parameter set, src/StereoBM/src/fpga.c:190-226
 SHIPPED_RECT = dict(
@@ -221,6 +224,104 @@ class Oracle:
         dp = ctypes.POINTER(ctypes.c_double)
         self.L.orc_reproject(disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), W, H, Pl.ctypes.data_as(dp),
                              Pr.ctypes.data_as(dp), decim, apply_local, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        return out
+
+    def reproject_ex(self, disp, P_l, P_r, decim=1, local_T=None, pose=None):
+        """dense consumer of main.cpp:522-551 with explicit 3x4 float transforms (None = skipped)"""
+        disp = np.ascontiguousarray(disp, np.int16)
+        H, W = disp.shape
+        Pl = np.ascontiguousarray(P_l, np.float64).reshape(12); Pr = np.ascontiguousarray(P_r, np.float64).reshape(12)
+        out = np.empty((H // decim, W // decim, 3), np.float32)
+        dp, fp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)
+        lt = None if local_T is None else np.ascontiguousarray(local_T, np.float32).reshape(12)
+        ps = None if pose is None else np.ascontiguousarray(pose, np.float32).reshape(12)
+        self.L.orc_reproject_ex.argtypes = [ctypes.POINTER(ctypes.c_int16), ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_int, fp, fp, fp]
+        self.L.orc_reproject_ex.restype = None
+        self.L.orc_reproject_ex(disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), W, H, Pl.ctypes.data_as(dp), Pr.ctypes.data_as(dp),
+                                decim, None if lt is None else lt.ctypes.data_as(fp), None if ps is None else ps.ctypes.data_as(fp),
+                                out.ctypes.data_as(fp))
+        return out
+
+    def reproject_points(self, disp, P_l, P_r, uv, min_depth=0.0, max_depth=0.0, local_T=LOCAL_TRANSFORM, mask=None):
+        """generateKeypoints3DStereo (Stereo.cpp:53-117) on a dense 16x disparity map; uv = (n, 2) float32 (x, y)"""
+        disp = np.ascontiguousarray(disp, np.int16)
+        H, W = disp.shape
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        n = uv.shape[0]
+        Pl = np.ascontiguousarray(P_l, np.float64).reshape(12); Pr = np.ascontiguousarray(P_r, np.float64).reshape(12)
+        out = np.empty((n, 3), np.float32)
+        dp, fp, u8p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint8)
+        lt = None if local_T is None else np.ascontiguousarray(local_T, np.float32).reshape(12)
+        mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self.L.orc_reproject_points.argtypes = [ctypes.POINTER(ctypes.c_int16), ctypes.c_int, ctypes.c_int, dp, dp, fp, ctypes.c_int, u8p,
+                                                ctypes.c_float, ctypes.c_float, fp, fp]
+        self.L.orc_reproject_points.restype = None
+        self.L.orc_reproject_points(disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), W, H, Pl.ctypes.data_as(dp), Pr.ctypes.data_as(dp),
+                                    uv.ctypes.data_as(fp), n, None if mk is None else mk.ctypes.data_as(u8p), min_depth, max_depth,
+                                    None if lt is None else lt.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        return out
+
+
+# ---- the reference's own 3-D code (Stereo.cpp, StereoCameraModel.cpp, Transform.cpp), compiled from /root/reference ----
+DEPTH_METHOD_CV_BM, DEPTH_METHOD_FPGA_BM = 2, 4        # enum DEPTH_METHOD, slam/include/core/Parameters.h:25-31
+
+
+class RefStereo:
+    """oracle/_ref/libstereo_ref.so (oracle/Makefile target `ref`): the reference's sources unmodified, OpenCV containers stubbed.
+    The camera model is loaded by the reference's own KITTI calib.txt reader, so every call takes the path of such a file."""
+
+    def __init__(self):
+        self.L = ctypes.CDLL(REF_STEREO_LIB_PATH)
+
+    @staticmethod
+    def write_kitti_calib(path, P_l, P_r):
+        with open(path, "w") as f:
+            for k, P in (("P0", P_l), ("P1", P_r)):
+                f.write(f"{k}: " + " ".join(repr(float(v)) for v in np.asarray(P, np.float64).reshape(12)) + "\n")
+
+    def model_load(self, calib, do_resize):
+        out = (ctypes.c_double * 10)()
+        rc = self.L.ref_model_load(calib.encode(), int(do_resize), out)
+        if rc != 0:
+            raise ValueError("StereoCameraModel::load failed")
+        v = list(out)
+        P_l = np.array([[v[0], 0, v[2], v[4]], [0, v[1], v[3], 0], [0, 0, 1, 0]], np.float64)
+        P_r = np.array([[v[5], 0, v[7], v[9]], [0, v[6], v[8], 0], [0, 0, 1, 0]], np.float64)
+        return P_l, P_r
+
+    def local_transform(self):
+        out = (ctypes.c_float * 12)()
+        is_null = self.L.ref_local_transform(out)
+        return np.array(list(out), np.float32), bool(is_null)
+
+    def keypoints3d(self, calib, do_resize, uv, disp, min_depth=0.0, max_depth=0.0, depth_method=DEPTH_METHOD_FPGA_BM):
+        disp = np.ascontiguousarray(disp, np.int16)
+        H, W = disp.shape
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.empty((uv.shape[0], 3), np.float32)
+        fp = ctypes.POINTER(ctypes.c_float)
+        self.L.ref_keypoints3d.argtypes = [ctypes.c_char_p, ctypes.c_int, fp, ctypes.c_int, ctypes.POINTER(ctypes.c_int16), ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, fp]
+        rc = self.L.ref_keypoints3d(calib.encode(), int(do_resize), uv.ctypes.data_as(fp), uv.shape[0],
+                                    disp.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), W, H, min_depth, max_depth, depth_method,
+                                    out.ctypes.data_as(fp))
+        if rc != 0:
+            raise ValueError("StereoCameraModel::load failed")
+        return out
+
+    def dense_cloud(self, calib, do_resize, depth, scale, apply_local=True, pose=None):
+        """main.cpp:522-551 over an already decimated map (SensorData.cpp:50-58) with dispScale = scale"""
+        depth = np.ascontiguousarray(depth, np.int16)
+        rows, cols = depth.shape
+        out = np.empty((rows, cols, 3), np.float32)
+        fp = ctypes.POINTER(ctypes.c_float)
+        ps = None if pose is None else np.ascontiguousarray(pose, np.float32).reshape(12)
+        self.L.ref_dense_cloud.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int16), ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, fp, fp]
+        rc = self.L.ref_dense_cloud(calib.encode(), int(do_resize), depth.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), rows, cols,
+                                    scale, int(apply_local), None if ps is None else ps.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        if rc != 0:
+            raise ValueError("StereoCameraModel::load failed")
         return out
 
 

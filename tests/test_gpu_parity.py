@@ -195,6 +195,148 @@ def test_reproject_matches_oracle(u, fe640, oracle):
             ((got == want) | (np.isnan(got) & np.isnan(want))).all()
 
 
+def _bits_equal(a, b):
+    return a.shape == b.shape and np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+def test_reproject_points_matches_oracle_and_reference_fixture(u, fe640, oracle):
+    """a16, keypoint form (generateKeypoints3DStereo, Stereo.cpp:53-117): GPU == oracle on 20 000 random keypoints per frame
+    of a real disparity batch (borders, invalid -1 pixels, out-of-map points, mask, depth gates, no / default / odd
+    localTransform), and GPU == the committed outputs of the reference's compiled code on the fixture's map."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import reproject_inputs
+    L, R = u.synth_batch(1, 4, 3, 640, 480, 64)
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    fe640.set_bm_params(x_store_offset=1)
+    fe640.submit_rect(1, L, R); b = fe640.wait()
+    d = fe640.receive_disp(b)
+    sx, sy = 640 / 1241, 480 / 376
+    P_l = np.array([[718.856 * sx, 0, 607.1928 * sx, 0], [0, 718.856 * sy, 185.2157 * sy, 0], [0, 0, 1, 0]])
+    P_r = P_l.copy(); P_r[0, 3] = -386.1448 * sx
+    rng = np.random.default_rng(7)
+    n = 20000
+    uv = np.stack([rng.random(n) * 640, rng.random(n) * 480], 1).astype(np.float32)
+    uv[:8] = [[0, 0], [639.99, 479.99], [-0.5, -0.5], [-1.0, 5], [640.0, 5], [5, 480.0], [np.nan, 3], [1e30, 1e30]]
+    uv[8:2000, 0] = rng.choice([0.0, 1.5, 74.2, 85.0, 86.0, 627.9, 628.0, 639.0], 1992)      # valid-rectangle borders (D + h, W - 2 - h + 1)
+    mask = (rng.random(n) < 0.9).astype(np.uint8)
+    odd_T = np.array([0.5, -0.25, 1.0, 0.125, -1.0, 0.0, 0.75, -2.0, 0.0, -1.0, 0.3, 4.0], np.float32)
+    total_good = 0
+    for f in range(3):
+        for (mn, mx, T, mk) in ((0.0, 0.0, u.LOCAL_TRANSFORM, None), (-1.0, 0.0, None, mask), (2.0, 12.0, odd_T, mask),
+                                (0.0, 4.0, np.zeros(12, np.float32), None)):
+            got = fe640.reproject_points(b, P_l, P_r, uv, f, mn, mx, T, mk)
+            want = oracle.reproject_points(d[f], P_l, P_r, uv, mn, mx, T, mk)
+            assert _bits_equal(got, want), (f, mn, mx)
+            total_good += int(np.isfinite(got[:, 0]).sum())
+        assert np.isnan(got[:8][[3, 4, 5, 6, 7]]).all()
+    assert total_good > 50000
+    # the reference's own outputs (fixture): upload its disparity map as a bank and gather
+    (W, H, disp, kuv, kP_l, kP_r, pose, gates) = reproject_inputs()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reproject_ref.npz"))
+    import torch
+    with u.StereoFrontEnd(0, W, H, 1) as fe:
+        fe.set_bm_params(width=W, height=H, profile=0, block_size=5, num_disparities=32)
+        z = np.zeros((1, H, W), np.uint8)
+        fe.submit_xsbl(0, z, z); fe.wait()
+        # overwrite the bank's disparity with the fixture's map (device pointer from the C ABI, wrapped zero-copy)
+        view = fe.disp_tensor(0)
+        view[0].copy_(torch.from_numpy(disp).cuda())
+        torch.cuda.synchronize()
+        for rs in (0, 1):
+            Pl, Pr = g[f"P_l_resize{rs}"], g[f"P_r_resize{rs}"]
+            for gi, (mn, mx) in enumerate(gates):
+                assert _bits_equal(fe.reproject_points(0, Pl, Pr, kuv, 0, mn, mx), g[f"kp_resize{rs}_gate{gi}"])
+            assert _bits_equal(fe.reproject_ex(0, Pl, Pr, 4, u.LOCAL_TRANSFORM, None)[0], g[f"dense_resize{rs}_local"])
+            assert _bits_equal(fe.reproject_ex(0, Pl, Pr, 4, u.LOCAL_TRANSFORM, pose[None])[0], g[f"dense_resize{rs}_local_pose"])
+        assert _bits_equal(fe.reproject_ex(0, g["P_l_resize0"], g["P_r_resize0"], 1, None, None)[0], g["dense_resize0_plain"])
+
+
+def test_reproject_ex_local_transform_and_per_frame_pose(u, fe640, oracle):
+    """dense consumer with both transforms (main.cpp:535-541), one pose per frame of the batch"""
+    L, R = u.synth_batch(1, 9, 4, 640, 480, 64)
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    fe640.set_bm_params(x_store_offset=1)
+    fe640.submit_rect(0, L, R); b = fe640.wait()
+    d = fe640.receive_disp(b)
+    sx, sy = 640 / 1241, 480 / 376
+    P_l = np.array([[718.856 * sx, 0, 607.1928 * sx, 0], [0, 718.856 * sy, 185.2157 * sy, 0], [0, 0, 1, 0]])
+    P_r = P_l.copy(); P_r[0, 3] = -386.1448 * sx
+    rng = np.random.default_rng(3)
+    poses = np.concatenate([rng.normal(size=(4, 3, 3)), rng.normal(size=(4, 3, 1)) * 5], 2).astype(np.float32).reshape(4, 12)
+    for decim in (1, 4, 8):
+        got = fe640.reproject_ex(b, P_l, P_r, decim, u.LOCAL_TRANSFORM, poses)
+        for f in range(4):
+            assert _bits_equal(got[f], oracle.reproject_ex(d[f], P_l, P_r, decim, u.LOCAL_TRANSFORM, poses[f])), (decim, f)
+    got = fe640.reproject_ex(b, P_l, P_r, 2, None, poses)
+    assert _bits_equal(got[3], oracle.reproject_ex(d[3], P_l, P_r, 2, None, poses[3]))
+    assert np.isfinite(got).any()
+
+
+def test_set_rect_image_then_software_start(u, fe640, oracle, golden):
+    """Fpga::setRectImage writes the RECT bank at call time (FPGA.cpp:236-249); FPGA_XSBL_SW_START runs xsbl -> bm on it"""
+    fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
+    fe640.set_bm_params(x_store_offset=1)
+    L, R = golden["rect_l"].copy(), golden["rect_r"].copy()
+    fe640.submit_rect(0, R, L); fe640.wait()                        # leave other contents in bank 0 first
+    fe640.set_rect_image(0, L, R)
+    keepL, keepR = L.copy(), R.copy()
+    L[:] = 0; R[:] = 0                                               # the caller's buffers are free again
+    rl, rr = fe640.receive_rect(0)
+    assert np.array_equal(rl[0], keepL) and np.array_equal(rr[0], keepR)
+    with pytest.raises(u.U96Error) as e:
+        fe640.receive_disp(0)                                        # nothing has run on this bank yet
+    assert e.value.code == -4
+    with pytest.raises(u.U96Error):
+        fe640.wait()                                                 # and nothing is in flight
+    fe640.start_xsbl(0)
+    assert fe640.wait() == 0
+    want = oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=64)
+    assert np.array_equal(fe640.receive_disp(0)[0], want)
+    xl, xr = fe640.receive_xsbl(0)
+    assert np.array_equal(xl[0], golden["xsbl_l"]) and np.array_equal(xr[0], golden["xsbl_r"])
+    f = u.Fpga(0)
+    assert f.registerOpen() == 0
+    f.setRectImage(1, keepL, keepR)
+    a, b2 = f.receiveRectImages(1)
+    assert np.array_equal(a, keepL) and np.array_equal(b2, keepR)
+    f.start(1)
+    bank, _, _, dm = f.receiveData()
+    assert bank == 1 and np.array_equal(dm, want)
+    f.registerClose()
+
+
+def test_configuration_is_locked_while_a_bank_is_in_flight_and_banks_keep_their_geometry(u, oracle):
+    """the setters refuse between submit and wait (a pending bank reads the map / tile plan / parameters); a
+    bank is received with the geometry it was filled with even after the configuration moved on."""
+    L, R = u.synth_batch(2, 0, 3, 640, 480, 64)
+    with u.StereoFrontEnd(0, 640, 480, 3) as fe:
+        fe.set_bm_params(width=640, height=480, profile=0, block_size=15, num_disparities=64, x_store_offset=1)
+        fe.set_rect_params(u.SHIPPED_RECT_PARAMS)
+        fe.submit_raw(0, L, R)
+        for call in (lambda: fe.set_bm_params(block_size=21), lambda: fe.set_rect_params(u.SHIPPED_RECT_PARAMS),
+                     lambda: fe.set_bm_registers((480 << 16) + 640, 0x00150040, 0), lambda: fe.set_stream(0)):
+            with pytest.raises(u.U96Error) as e:
+                call()
+            assert e.value.code == -4
+        assert fe.get_bm_params()["block_size"] == 15
+        assert fe.wait() == 0
+        want = [oracle.bm_rtl(oracle.xsobel_rtl(oracle.rectify(L[i], u.SHIPPED_RECT_PARAMS, 0)),
+                              oracle.xsobel_rtl(oracle.rectify(R[i], u.SHIPPED_RECT_PARAMS, 1)), wsz=15, ndisp=64) for i in range(3)]
+        fe.set_bm_params(width=320, height=240, block_size=9, num_disparities=32)       # idle now: accepted
+        l2, r2 = u.synth_batch(3, 0, 2, 320, 240, 32)
+        fe.submit_rect(1, l2, r2); assert fe.wait() == 1
+        d0 = fe.receive_disp(0)                                      # bank 0 still holds three 640x480 maps
+        assert d0.shape == (3, 480, 640)
+        for i in range(3):
+            assert np.array_equal(d0[i], want[i])
+        rl, _ = fe.receive_rect(0)
+        assert rl.shape == (3, 480, 640) and np.array_equal(rl[1], oracle.rectify(L[1], u.SHIPPED_RECT_PARAMS, 0))
+        d1 = fe.receive_disp(1)
+        assert d1.shape == (2, 240, 320)
+        assert np.array_equal(d1[0], oracle.bm_rtl(oracle.xsobel_rtl(l2[0]), oracle.xsobel_rtl(r2[0]), wsz=9, ndisp=32))
+
+
 def test_error_behaviour(u):
     with u.StereoFrontEnd(0, 320, 240, 2) as fe:
         with pytest.raises(u.U96Error) as e:
@@ -247,9 +389,12 @@ def test_cpp_host_shim(u):
         g.build()
     out = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
-    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("frame")]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("kpts3d")]
     assert len(lines) == 3
     for i, ln in enumerate(lines):
+        kf, ln = ln.split(";", 1)
+        kf = kf.split()                                              # generateKeypoints3D (Stereo.cpp:119-154) through Fpga.hpp
+        assert int(kf[3]) > 100 and int(kf[5]) == int(kf[3]) and int(kf[1]) > 0.5 * int(kf[3])
         f = ln.split()
         assert int(f[3]) == i % 2                                    # bank = iteration % 2 (main.cpp:168)
         assert float(f[f.index("frac_at_12px") + 1]) > 0.95          # random texture shifted by 12 px

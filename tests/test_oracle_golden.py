@@ -5,7 +5,7 @@ import zlib
 import numpy as np
 import pytest
 
-from oracle_py import SHIPPED_RECT, REF_LIB_PATH, RefFpga
+from oracle_py import SHIPPED_RECT, REF_LIB_PATH, REF_STEREO_LIB_PATH, RefFpga
 
 
 def test_kat1_xsobel_matches_reference_golden(oracle, golden):
@@ -193,6 +193,82 @@ def test_reproject_matches_float_formula(oracle):
         assert np.array_equal(out[..., 2][~bad], Z[~bad]) and np.array_equal(out[..., 0][~bad], X[~bad])
         loc = oracle.reproject(disp, P_l, P_r, decim, 1)
         assert np.array_equal(loc[..., 0][~bad], out[..., 2][~bad]) and np.array_equal(loc[..., 1][~bad], -out[..., 0][~bad])
+
+
+def _reproject_fixture():
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_golden import reproject_inputs
+    g = np.load(os.path.join(here, "golden", "reproject_ref.npz"))
+    return reproject_inputs(), {k: g[k] for k in g.files}
+
+
+def _same_bits(a, b):
+    return a.shape == b.shape and np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+def test_reprojection_oracle_matches_reference_fixture(oracle):
+    """a16 pinned: the oracle equals the outputs of the reference's own Stereo.cpp / StereoCameraModel.cpp / Transform.cpp
+    (compiled unmodified, fixture made by tests/golden/make_golden.py) bit for bit, NaNs and signed zeros included."""
+    import u96_slam_b200 as u
+    (W, H, disp, uv, P_l, P_r, pose, gates), g = _reproject_fixture()
+    assert np.array_equal(g["local_transform"], u.LOCAL_TRANSFORM)
+    for rs in (0, 1):
+        Pl, Pr = g[f"P_l_resize{rs}"], g[f"P_r_resize{rs}"]
+        for gi, (mn, mx) in enumerate(gates):
+            want = g[f"kp_resize{rs}_gate{gi}"]
+            assert _same_bits(oracle.reproject_points(disp, Pl, Pr, uv, mn, mx), want)
+            assert np.isfinite(want[:, 0]).sum() > (0 if (rs, gi) == (0, 3) else 200)
+        assert _same_bits(oracle.reproject_ex(disp, Pl, Pr, 4, u.LOCAL_TRANSFORM, None), g[f"dense_resize{rs}_local"])
+        assert _same_bits(oracle.reproject_ex(disp, Pl, Pr, 4, u.LOCAL_TRANSFORM, pose), g[f"dense_resize{rs}_local_pose"])
+    assert _same_bits(oracle.reproject_ex(disp, g["P_l_resize0"], g["P_r_resize0"], 1, None, None), g["dense_resize0_plain"])
+    # the legacy entry point = localTransform through transformPoint
+    assert _same_bits(oracle.reproject(disp, g["P_l_resize1"], g["P_r_resize1"], 4, 1), g["dense_resize1_local"])
+
+
+def test_kitti_projection_loader_matches_reference_fixture(tmp_path):
+    """formats.load_projection_kitti == StereoCameraModel::load (KITTI route + 640x480 rescale, StereoCameraModel.cpp:68-119)"""
+    import u96_slam_b200 as u
+    from oracle_py import RefStereo
+    (W, H, disp, uv, P_l, P_r, pose, gates), g = _reproject_fixture()
+    calib = str(tmp_path / "calib.txt")
+    RefStereo.write_kitti_calib(calib, P_l, P_r)
+    for rs in (0, 1):
+        Pl, Pr = u.load_projection_kitti(calib, do_resize=bool(rs))
+        for mine, ref in ((Pl, g[f"P_l_resize{rs}"]), (Pr, g[f"P_r_resize{rs}"])):
+            for (i, j) in ((0, 0), (1, 1), (0, 2), (1, 2), (0, 3)):      # the ten getters of StereoCameraModel.h:24-33
+                assert mine[i, j] == ref[i, j]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_STEREO_LIB_PATH), reason="oracle/_ref/libstereo_ref.so not built (reference tree absent)")
+def test_reprojection_oracle_matches_live_compiled_reference(oracle, tmp_path):
+    """The same pin on fresh random inputs: oracle == the reference's compiled functions, called live."""
+    from oracle_py import RefStereo, LOCAL_TRANSFORM
+    r = RefStereo()
+    t, is_null = r.local_transform()
+    assert not is_null and np.array_equal(t, LOCAL_TRANSFORM)
+    rng = np.random.default_rng(11)
+    for trial in range(3):
+        W, H = (640, 480) if trial == 0 else (int(rng.integers(40, 300)), int(rng.integers(30, 200)))
+        fx = float(rng.uniform(300, 900)); fy = fx * float(rng.uniform(0.9, 1.1))
+        P_l = np.array([[fx, 0, W * rng.uniform(0.4, 0.6), 0], [0, fy, H * rng.uniform(0.4, 0.6), 0], [0, 0, 1, 0]], np.float64)
+        P_r = P_l.copy(); P_r[0, 3] = -fx * rng.uniform(0.05, 0.6); P_r[0, 2] += (0.0 if trial < 2 else 3.5)
+        calib = str(tmp_path / f"calib{trial}.txt")
+        r.write_kitti_calib(calib, P_l, P_r)
+        Pl, Pr = r.model_load(calib, trial == 1)
+        disp = rng.integers(-64, 256 * 16, (H, W)).astype(np.int16)
+        disp[rng.random((H, W)) < 0.3] = -1
+        n = 12000 if trial == 0 else 3000
+        uv = np.stack([rng.random(n) * W, rng.random(n) * H], 1).astype(np.float32)
+        uv[:3] = [[0, 0], [W - 0.001, H - 0.001], [-0.25, -0.75]]
+        for mn, mx in ((0.0, 0.0), (-1.0, 0.0), (1.0, 20.0), (0.0, 3.0)):
+            assert _same_bits(oracle.reproject_points(disp, Pl, Pr, uv, mn, mx), r.keypoints3d(calib, trial == 1, uv, disp, mn, mx))
+        pose = np.concatenate([rng.normal(size=(3, 3)), rng.normal(size=(3, 1)) * 3], 1).astype(np.float32).reshape(12)
+        dd = np.ascontiguousarray(disp[::4, ::4][:H // 4, :W // 4])
+        assert _same_bits(oracle.reproject_ex(disp, Pl, Pr, 4, LOCAL_TRANSFORM, pose), r.dense_cloud(calib, trial == 1, dd, 4, True, pose))
+        assert _same_bits(oracle.reproject_ex(disp, Pl, Pr, 1, None, None), r.dense_cloud(calib, trial == 1, disp, 1, False, None))
 
 
 def test_postfilters_match_opencv_public_functions(oracle, golden, cv_golden):

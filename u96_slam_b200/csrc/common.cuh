@@ -56,8 +56,14 @@ int launch_bm_fast_cs4(const uint8_t *xl, const uint8_t *xr, int pitch, size_t f
 int launch_postfilter(Img16 disp, const int16_t *cost, int W, int H, int n, int ndisp, int disp12_max_diff,
                       int speckle_window, int speckle_range, int *scratch, cudaStream_t s);
 
+// local_T: 3x4 row-major float transform (host; null or all zero = none); d_poses: n x 12 floats in device memory or null
 int launch_reproject(const int16_t *disp, int dpitch, size_t dframe, int W, int H, int n,
-                     const double *P_l, const double *P_r, int decim, int flags, float *xyz, cudaStream_t s);
+                     const double *P_l, const double *P_r, int decim, const float *local_T, const float *d_poses,
+                     float *xyz, cudaStream_t s);
+// generateKeypoints3DStereo on one frame's disparity map; d_uv = n float pairs (x, y), d_mask = n bytes or null (device)
+int launch_reproject_points(const int16_t *disp, int dpitch, int W, int H, const double *P_l, const double *P_r,
+                            const float *d_uv, const uint8_t *d_mask, int n, float min_depth, float max_depth,
+                            const float *local_T, float *xyz, cudaStream_t s);
 
 // UVC payload (xusb_main.c:293-376): YUYV frame of 2W x H; disp != null selects the disparity mode
 int launch_pack_uvc(const uint8_t *srcL, const uint8_t *srcR, int sp, size_t sf, const int16_t *disp, int dp, size_t df,

@@ -117,6 +117,8 @@ int launch_postfilter(Img16 disp, const int16_t *cost, int W, int H, int n, int 
 {
     int launches = 0;
     if (disp12_max_diff >= 0 && cost) {
+        if (W * sizeof(unsigned long long) > 48 * 1024)          // rows wider than 6144 px need the opt-in shared-memory carve-out
+            cudaFuncSetAttribute(k_validate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W * sizeof(unsigned long long)));
         k_validate<<<dim3(H, n), 256, W * sizeof(unsigned long long), s>>>(disp.p, cost, disp.pitch, disp.frame, W, ndisp, disp12_max_diff * 16);
         launches++;
     }

@@ -51,6 +51,8 @@ cudaError_t copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, siz
 }
 
 enum { FROM_RAW = 0, FROM_RECT = 1, FROM_XSBL = 2 };
+// per-stage events of a submit: start | h2d | rect | gftt | xsbl | bm | post filters
+constexpr int NEV = U96_STAGE_COUNT + 1;
 
 struct Bank {
     uint8_t *raw[2] = {nullptr, nullptr}, *rect[2] = {nullptr, nullptr}, *xsbl[2] = {nullptr, nullptr};
@@ -68,11 +70,14 @@ struct Bank {
     int raw_pitch = 0, rect_pitch = 0, xsbl_pitch = 0;
     size_t raw_frame = 0, rect_frame = 0, xsbl_frame = 0;
     int n = 0, from = -1;
+    int W = 0, H = 0;                   // geometry the bank was filled with (snapshot at submit: receive / reproject / uvc use these)
     bool filled = false, pending = false;
+    bool has_disp = false;              // the kernels ran (false after u96_set_rect_image until u96_start_xsbl)
+    bool staged = false;                // pipelined submit: per-stage events were not recorded
     cudaStream_t stream = nullptr;
     cudaStream_t sub[3] = {nullptr, nullptr, nullptr};      // chunk pipeline: H2D / kernels / D2H of different chunks overlap
     cudaEvent_t sub_ev[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t done = nullptr, ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done = nullptr, ev[NEV] = {};
 };
 
 }  // namespace
@@ -94,7 +99,15 @@ struct u96_handle {
     size_t xyz_cap = 0;
     uint8_t *uvc = nullptr;
     size_t uvc_cap = 0;
+    float *kp = nullptr;           // keypoint scratch: uv (2n floats) | xyz (3n floats) | mask (n bytes)
+    size_t kp_cap = 0;
+    float *poses = nullptr;        // dense reprojection: one 3x4 pose per frame
+    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    float aux_ms[U96_AUX_COUNT] = {};
+    bool aux_valid[U96_AUX_COUNT] = {};
 };
+
+static bool any_pending(const u96_handle *h) { return h->bank[0].pending || h->bank[1].pending; }
 
 static int validate_bm(const u96_handle *h, const u96_bm_params &p)
 {
@@ -117,6 +130,7 @@ static int validate_bm(const u96_handle *h, const u96_bm_params &p)
         if (p.uniqueness_ratio < 0 || p.texture_threshold < 0) return U96_ERR_INVALID;
         if (p.speckle_window_size < 0 || p.speckle_window_size > 1000000) return U96_ERR_INVALID;
         if (p.width - p.num_disparities + 1 - 2 * hw <= 0) return U96_ERR_INVALID;
+        if (p.disp12_max_diff >= 0 && (size_t)p.width * 8 > 227 * 1024) return U96_ERR_UNSUPPORTED;   // k_validate keeps one row of keys in shared memory
         max_ad = 2 * p.prefilter_cap;
     } else return U96_ERR_INVALID;
     if (p.height - 2 * hw <= 0) return U96_ERR_INVALID;
@@ -188,9 +202,11 @@ int u96_create(u96_handle **out, int device, int max_w, int max_h, int max_batch
         for (int i = 0; i < 3; i++)
             if (cudaStreamCreateWithFlags(&k.sub[i], cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&k.sub_ev[i], cudaEventDisableTiming) != cudaSuccess) return fail(U96_ERR_CUDA);
-        for (int i = 0; i < 5; i++)
+        for (int i = 0; i < NEV; i++)
             if (cudaEventCreate(&k.ev[i]) != cudaSuccess) return fail(U96_ERR_CUDA);
     }
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreate(&h->aux_ev[i]) != cudaSuccess) return fail(U96_ERR_CUDA);
     if (cudaMalloc(&h->map, sizeof(int2) * 2 * (size_t)max_w * max_h) != cudaSuccess) return fail(U96_ERR_NOMEM);
     // defaults = what the firmware programs (fpga.c:150-160): 640x480, wsz 21, 64 disparities, uniqueness off
     u96_bm_params d{};
@@ -217,7 +233,7 @@ void u96_destroy(u96_handle *h)
         cudaFree(k.eig);
         cudaFree(k.eig_max);
         if (k.done) cudaEventDestroy(k.done);
-        for (int i = 0; i < 5; i++) if (k.ev[i]) cudaEventDestroy(k.ev[i]);
+        for (int i = 0; i < NEV; i++) if (k.ev[i]) cudaEventDestroy(k.ev[i]);
         for (int i = 0; i < 3; i++) { if (k.sub_ev[i]) cudaEventDestroy(k.sub_ev[i]); if (k.sub[i]) { cudaStreamSynchronize(k.sub[i]); cudaStreamDestroy(k.sub[i]); } }
         if (k.stream) cudaStreamDestroy(k.stream);
     }
@@ -225,6 +241,9 @@ void u96_destroy(u96_handle *h)
     rect_plan_free(h->plan);
     cudaFree(h->xyz);
     cudaFree(h->uvc);
+    cudaFree(h->kp);
+    cudaFree(h->poses);
+    for (int i = 0; i < 2; i++) if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
     delete h;
 }
 
@@ -233,6 +252,9 @@ int u96_set_bm_params(u96_handle *h, const u96_bm_params *p)
     if (!h || !p) return U96_ERR_INVALID;
     const int rc = validate_bm(h, *p);
     if (rc != U96_OK) return rc;
+    // a bank in flight still reads the current configuration (and, through the map and the tile plan, the geometry):
+    // like the FPGA's registers, the parameters may only change while the pipeline is idle
+    if (any_pending(h)) return U96_ERR_STATE;
     if (p->width != h->bm.width || p->height != h->bm.height) h->map_valid = false;
     h->bm = *p;
     return U96_OK;
@@ -264,6 +286,7 @@ int u96_get_bm_params(u96_handle *h, u96_bm_params *p)
 int u96_set_rect_params(u96_handle *h, const u96_rect_params *p)
 {
     if (!h || !p) return U96_ERR_INVALID;
+    if (any_pending(h)) return U96_ERR_STATE;                 // the pending bank's remap kernel reads the map this call invalidates
     h->rect = *p;
     h->rect_set = true;
     h->map_valid = false;
@@ -273,6 +296,7 @@ int u96_set_rect_params(u96_handle *h, const u96_rect_params *p)
 int u96_set_stream(u96_handle *h, void *cuda_stream)
 {
     if (!h) return U96_ERR_INVALID;
+    if (any_pending(h)) return U96_ERR_STATE;
     h->user_stream = (cudaStream_t)cuda_stream;
     h->use_user_stream = true;
     return U96_OK;
@@ -301,18 +325,18 @@ static cudaStream_t bank_stream(u96_handle *h, int bank) { return h->use_user_st
 
 // Tight staging area of a bank (see copy2d): L | R | 16-bit output, each for maxB frames of the current geometry.  Only
 // needed when the image width differs from the internal pitch; the bank must be idle when it grows.
-static int ensure_stage(u96_handle *h, Bank &k)
+static int ensure_stage(u96_handle *h, Bank &k, int W, int H)
 {
-    const size_t px = (size_t)h->bm.width * h->bm.height * h->maxB;
-    if (h->bm.width == h->pitch) return U96_OK;               // contiguous transfers anyway
+    const size_t px = (size_t)W * H * h->maxB;
+    if (W == h->pitch) return U96_OK;                         // contiguous transfers anyway
     if (k.stage_cap >= 4 * px) return U96_OK;
     cudaFree(k.stage); k.stage = nullptr; k.stage_cap = 0;
     if (cudaMalloc(&k.stage, 4 * px) != cudaSuccess) return U96_ERR_NOMEM;
     k.stage_cap = 4 * px;
     return U96_OK;
 }
-static uint8_t *stage_in(u96_handle *h, Bank &k, int i) { return k.stage ? k.stage + (size_t)i * h->bm.width * h->bm.height * h->maxB : nullptr; }
-static uint8_t *stage_out(u96_handle *h, Bank &k) { return k.stage ? k.stage + (size_t)2 * h->bm.width * h->bm.height * h->maxB : nullptr; }
+static uint8_t *stage_in(u96_handle *h, Bank &k, int i) { return k.stage ? k.stage + (size_t)i * k.W * k.H * h->maxB : nullptr; }
+static uint8_t *stage_out(u96_handle *h, Bank &k) { return k.stage ? k.stage + (size_t)2 * k.W * k.H * h->maxB : nullptr; }
 
 static int ensure_map(u96_handle *h, cudaStream_t s)
 {
@@ -322,7 +346,7 @@ static int ensure_map(u96_handle *h, cudaStream_t s)
     rp.p = h->rect; rp.W = h->bm.width; rp.H = h->bm.height;
     rp.wrap16 = (rp.W <= 1023 && rp.H <= 511) ? 1 : 0;      // RTL counter widths; beyond = RTL-extended
     h->launches += launch_rect_build_map(rp, h->map, s);
-    rect_plan_free(h->plan);
+    rect_plan_free(h->plan);                                  // no bank is in flight here: the setters refuse while one is pending
     h->launches += rect_plan_build(h->plan, h->map, rp.W, rp.H, s);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));                             // other bank's stream may use the map next
@@ -330,10 +354,32 @@ static int ensure_map(u96_handle *h, cudaStream_t s)
     return U96_OK;
 }
 
+// lazily allocated per-bank buffers the current configuration needs; called before anything is enqueued
+static int ensure_bank_buffers(u96_handle *h, Bank &k, int from, int n, bool host_src)
+{
+    const int W = h->bm.width, H = h->bm.height, pitch = h->pitch;
+    const bool cv = (h->bm.profile == U96_PROFILE_OPENCV);
+    if (cv && h->bm.disp12_max_diff >= 0 && !k.cost)
+        if (cudaMalloc(&k.cost, (size_t)pitch * h->maxH * h->maxB * sizeof(int16_t)) != cudaSuccess) return U96_ERR_NOMEM;
+    if (cv && h->bm.speckle_window_size > 0) {
+        const size_t need = (size_t)2 * n * W * H;
+        if (need > k.cc_cap) {                                // the bank is idle here (not pending)
+            cudaFree(k.cc); k.cc = nullptr; k.cc_cap = 0;
+            if (cudaMalloc(&k.cc, need * sizeof(int)) != cudaSuccess) return U96_ERR_NOMEM;
+            k.cc_cap = need;
+        }
+    }
+    if (h->gftt && from <= FROM_RECT && !k.eig)
+        if (cudaMalloc(&k.eig, (size_t)pitch * h->maxH * h->maxB * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMalloc(&k.eig_max, (size_t)h->maxB * sizeof(uint32_t)) != cudaSuccess) return U96_ERR_NOMEM;
+    if (host_src) return ensure_stage(h, k, W, H);
+    return U96_OK;
+}
+
 // kernels of frames [f0, f0+nf) of a bank on stream s; `prof` records the Perf-style stage events
 static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStream_t s, bool prof)
 {
-    const int W = h->bm.width, H = h->bm.height, pitch = h->pitch;
+    const int W = k.W, H = k.H, pitch = h->pitch;
     const size_t frame = (size_t)pitch * H, o = (size_t)f0 * frame;
     const Img8 rectL{k.rect[0] + o, pitch, frame}, rectR{k.rect[1] + o, pitch, frame};
     const Img8 xsblL{k.xsbl[0] + o, pitch, frame}, xsblR{k.xsbl[1] + o, pitch, frame};
@@ -341,14 +387,15 @@ static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStrea
     if (from == FROM_RAW)
         h->launches += launch_rect_remap(k.cur_raw[0] + (size_t)f0 * k.raw_frame, k.cur_raw[1] + (size_t)f0 * k.raw_frame, k.raw_pitch,
                                          k.raw_frame, rectL, rectR, h->map, h->plan, W, H, nf, s);
+    if (prof) CK(cudaEventRecord(k.ev[2], s));
     if (h->gftt && from <= FROM_RECT)                        // the GFTT block reads the RECT bank (fpga.c:166-167)
         h->launches += launch_gftt(k.cur_rect[0] + (size_t)f0 * k.rect_frame, k.rect_pitch, k.rect_frame, k.eig + o, pitch, frame,
                                    k.eig_max + f0, W, H, nf, s);
-    if (prof) CK(cudaEventRecord(k.ev[2], s));
+    if (prof) CK(cudaEventRecord(k.ev[3], s));
     if (from <= FROM_RECT)
         h->launches += launch_xsobel(k.cur_rect[0] + (size_t)f0 * k.rect_frame, k.cur_rect[1] + (size_t)f0 * k.rect_frame, k.rect_pitch,
                                      k.rect_frame, xsblL, xsblR, W, H, nf, h->bm.profile, h->bm.prefilter_cap, s);
-    if (prof) CK(cudaEventRecord(k.ev[3], s));
+    if (prof) CK(cudaEventRecord(k.ev[4], s));
     BmConfig cfg = bm_config(h->bm);
     const bool cv = (h->bm.profile == U96_PROFILE_OPENCV);
     const bool want_validate = cv && h->bm.disp12_max_diff >= 0;
@@ -356,19 +403,43 @@ static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStrea
     if (want_validate) cfg.cost = k.cost + o;
     h->launches += launch_bm(k.cur_xsbl[0] + (size_t)f0 * k.xsbl_frame, k.cur_xsbl[1] + (size_t)f0 * k.xsbl_frame, k.xsbl_pitch,
                              k.xsbl_frame, disp, cfg, nf, s);
+    if (prof) CK(cudaEventRecord(k.ev[5], s));
     if (want_validate || want_speckle)                       // cv::StereoBM::compute post filters (main.cpp:210-212)
         h->launches += launch_postfilter(disp, want_validate ? k.cost + o : nullptr, W, H, nf, h->bm.num_disparities,
                                          want_validate ? h->bm.disp12_max_diff : -1, want_speckle ? h->bm.speckle_window_size : 0,
                                          h->bm.speckle_range, want_speckle ? k.cc + (size_t)2 * f0 * W * H : nullptr, s);
-    if (prof) CK(cudaEventRecord(k.ev[4], s));
+    if (prof) CK(cudaEventRecord(k.ev[6], s));
     return U96_OK;
 }
+
+// A submit failed after work was already enqueued: drain everything the bank has in flight so that a retry cannot overwrite
+// buffers that are still being read, then hand the error back.  The bank stays idle (not pending, not filled).
+static int abort_submit(u96_handle *h, Bank &k, cudaStream_t s, int rc)
+{
+    const std::string first = g_cuda_err;
+    for (int i = 0; i < 3; i++) cudaStreamSynchronize(k.sub[i]);
+    cudaStreamSynchronize(s);
+    cudaGetLastError();
+    g_cuda_err = first;
+    k.filled = false; k.has_disp = false;
+    (void)h;
+    return rc;
+}
+#define CKA(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            g_cuda_err = std::string(#call) + ": " + cudaGetErrorString(e__);             \
+            return abort_submit(h, k, s, U96_ERR_CUDA);                                   \
+        }                                                                                 \
+    } while (0)
 
 // device_src: pointers are device memory (zero-copy when aligned).  disp_out (host, optional): the disparity is
 // copied out behind the kernels; large host batches are cut into chunks that flow through three sub-streams so
 // the H2D copy, the kernels and the D2H copy of different chunks overlap (both copy engines + SMs busy).
+// upload_only: Fpga::setRectImage -- the pair lands in the RECT bank and nothing runs until u96_start_xsbl.
 static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, const uint8_t *R, int stride, int n, bool device_src,
-                         int16_t *disp_out = nullptr)
+                         int16_t *disp_out = nullptr, bool upload_only = false)
 {
     if (!h || !L || !R || bank < 0 || bank > 1 || n <= 0 || n > h->maxB) return U96_ERR_INVALID;
     const int W = h->bm.width, H = h->bm.height;
@@ -379,13 +450,15 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     cudaStream_t s = bank_stream(h, bank);
     const int pitch = h->pitch;
     const size_t frame = (size_t)pitch * H;
+    // ---- everything that can fail without touching the GPU queues comes first ----
     if (from == FROM_RAW) { const int rc = ensure_map(h, s); if (rc != U96_OK) return rc; }
-    if (h->profiling) CK(cudaEventRecord(k.ev[0], s));
+    k.W = W; k.H = H;
+    { const int rc = ensure_bank_buffers(h, k, from, n, !device_src); if (rc != U96_OK) return rc; }
 
     uint8_t *dstbuf[2];
     for (int i = 0; i < 2; i++) dstbuf[i] = (from == FROM_RAW) ? k.raw[i] : (from == FROM_RECT) ? k.rect[i] : k.xsbl[i];
     const uint8_t *src[2] = {L, R};
-    const bool zero_copy = device_src && (stride % 16 == 0) && (stride >= align_up(W, 16)) &&
+    const bool zero_copy = device_src && !upload_only && (stride % 16 == 0) && (stride >= align_up(W, 16)) &&
                            (((uintptr_t)L | (uintptr_t)R) % 16 == 0);
     const uint8_t *cur[2] = {zero_copy ? L : dstbuf[0], zero_copy ? R : dstbuf[1]};
     const int cur_pitch = zero_copy ? stride : pitch;
@@ -398,36 +471,30 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     }
     if (from <= FROM_RECT) { k.cur_xsbl[0] = k.xsbl[0]; k.cur_xsbl[1] = k.xsbl[1]; k.xsbl_pitch = pitch; k.xsbl_frame = frame; }
     else { k.cur_xsbl[0] = cur[0]; k.cur_xsbl[1] = cur[1]; k.xsbl_pitch = cur_pitch; k.xsbl_frame = cur_frame; }
+    k.has_eig = h->gftt && from <= FROM_RECT && !upload_only;
+    k.n = n; k.from = from;
 
-    if (h->bm.profile == U96_PROFILE_OPENCV && h->bm.disp12_max_diff >= 0 && !k.cost) {
-        if (cudaMalloc(&k.cost, (size_t)pitch * H * h->maxB * sizeof(int16_t)) != cudaSuccess) return U96_ERR_NOMEM;
-    }
-    if (h->bm.profile == U96_PROFILE_OPENCV && h->bm.speckle_window_size > 0) {
-        const size_t need = (size_t)2 * n * W * H;
-        if (need > k.cc_cap) {                                // the bank is idle here (not pending)
-            cudaFree(k.cc); k.cc = nullptr; k.cc_cap = 0;
-            if (cudaMalloc(&k.cc, need * sizeof(int)) != cudaSuccess) return U96_ERR_NOMEM;
-            k.cc_cap = need;
-        }
-    }
-    if (h->gftt && from <= FROM_RECT && !k.eig) {
-        if (cudaMalloc(&k.eig, (size_t)pitch * H * h->maxB * sizeof(uint16_t)) != cudaSuccess ||
-            cudaMalloc(&k.eig_max, (size_t)h->maxB * sizeof(uint32_t)) != cudaSuccess) return U96_ERR_NOMEM;
-    }
-    k.has_eig = h->gftt && from <= FROM_RECT;
-    const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= 64;
-    if (!device_src) { const int rc = ensure_stage(h, k); if (rc != U96_OK) return rc; }
+    // ---- from here on work is enqueued: errors drain the bank before they are returned (abort_submit) ----
+    const bool prof = h->profiling && !upload_only;
+    if (prof) CKA(cudaEventRecord(k.ev[0], s));
+    const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= 64 && !upload_only;
+    k.staged = pipelined;
     if (!pipelined) {
         if (!zero_copy)
             for (int i = 0; i < 2; i++)
-                CK(copy2d(dstbuf[i], pitch, src[i], stride, W, (size_t)H * n,
-                                     device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s, device_src ? nullptr : stage_in(h, k, i)));
-        if (h->profiling) CK(cudaEventRecord(k.ev[1], s));
-        const int rc = run_range(h, k, from, 0, n, s, h->profiling);
-        if (rc != U96_OK) return rc;
+                CKA(copy2d(dstbuf[i], pitch, src[i], stride, W, (size_t)H * n,
+                           device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s, device_src ? nullptr : stage_in(h, k, i)));
+        if (upload_only) {
+            CKA(cudaStreamSynchronize(s));                    // like the memcpy of FPGA.cpp:236-249: the caller may reuse its buffers
+            k.filled = true; k.has_disp = false;
+            return U96_OK;
+        }
+        if (prof) CKA(cudaEventRecord(k.ev[1], s));
+        const int rc = run_range(h, k, from, 0, n, s, prof);
+        if (rc != U96_OK) return abort_submit(h, k, s, rc);
         if (disp_out)
-            CK(copy2d(disp_out, (size_t)W * 2, k.disp, (size_t)pitch * 2, (size_t)W * 2, (size_t)H * n, cudaMemcpyDeviceToHost, s,
-                      device_src ? nullptr : stage_out(h, k)));
+            CKA(copy2d(disp_out, (size_t)W * 2, k.disp, (size_t)pitch * 2, (size_t)W * 2, (size_t)H * n, cudaMemcpyDeviceToHost, s,
+                       device_src ? nullptr : stage_out(h, k)));
     } else {
         // chunks of whole BM waves (a chunk that fills half the SMs would make the kernels, not PCIe, the bottleneck)
         const int wave = bm_wave_frames(bm_config(h->bm));
@@ -435,50 +502,60 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
         static const int csz_env = getenv("U96_CHUNK") ? atoi(getenv("U96_CHUNK")) : 0;     // developer override (frames per chunk)
         if (csz_env > 0) csz = csz_env;
         if (csz > n) csz = n;
-        CK(cudaEventRecord(k.done, s));                       // the sub-streams start behind whatever the bank stream holds
-        for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(k.sub[i], k.done, 0));
+        CKA(cudaEventRecord(k.done, s));                      // the sub-streams start behind whatever the bank stream holds
+        for (int i = 0; i < 3; i++) CKA(cudaStreamWaitEvent(k.sub[i], k.done, 0));
         for (int c = 0, f0 = 0; f0 < n; c++, f0 += csz) {
             const int nf = std::min(csz, n - f0);
             cudaStream_t cs = k.sub[c % 3];
             for (int i = 0; i < 2; i++)
-                CK(copy2d(dstbuf[i] + (size_t)f0 * frame, pitch, src[i] + (size_t)f0 * stride * H, stride, W, (size_t)H * nf,
-                                     cudaMemcpyHostToDevice, cs, k.stage ? stage_in(h, k, i) + (size_t)f0 * W * H : nullptr));
+                CKA(copy2d(dstbuf[i] + (size_t)f0 * frame, pitch, src[i] + (size_t)f0 * stride * H, stride, W, (size_t)H * nf,
+                           cudaMemcpyHostToDevice, cs, k.stage ? stage_in(h, k, i) + (size_t)f0 * W * H : nullptr));
             const int rc = run_range(h, k, from, f0, nf, cs, false);
-            if (rc != U96_OK) return rc;
+            if (rc != U96_OK) return abort_submit(h, k, s, rc);
             if (disp_out)
-                CK(copy2d(disp_out + (size_t)f0 * W * H, (size_t)W * 2, k.disp + (size_t)f0 * frame, (size_t)pitch * 2,
-                                     (size_t)W * 2, (size_t)H * nf, cudaMemcpyDeviceToHost, cs,
-                                     k.stage ? stage_out(h, k) + (size_t)f0 * W * H * 2 : nullptr));
+                CKA(copy2d(disp_out + (size_t)f0 * W * H, (size_t)W * 2, k.disp + (size_t)f0 * frame, (size_t)pitch * 2,
+                           (size_t)W * 2, (size_t)H * nf, cudaMemcpyDeviceToHost, cs,
+                           k.stage ? stage_out(h, k) + (size_t)f0 * W * H * 2 : nullptr));
         }
         for (int i = 0; i < 3; i++) {                         // join: the bank stream (and `done`) follows all chunks
-            CK(cudaEventRecord(k.sub_ev[i], k.sub[i]));
-            CK(cudaStreamWaitEvent(s, k.sub_ev[i], 0));
+            CKA(cudaEventRecord(k.sub_ev[i], k.sub[i]));
+            CKA(cudaStreamWaitEvent(s, k.sub_ev[i], 0));
         }
     }
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(k.done, s));
-    k.n = n; k.from = from; k.filled = true; k.pending = true;
+    CKA(cudaGetLastError());
+    CKA(cudaEventRecord(k.done, s));
+    k.filled = true; k.has_disp = true; k.pending = true;
     h->fifo.push_back(bank);
     return U96_OK;
 }
 
-static int receive_u8(u96_handle *h, int bank, const uint8_t *const cur[2], int pitch, size_t frame, int min_from,
-                      uint8_t *L, uint8_t *R)
+static int receive_u8(u96_handle *h, int bank, const uint8_t *const cur[2], int pitch, int min_from, uint8_t *L, uint8_t *R)
 {
     if (!h || bank < 0 || bank > 1 || !L || !R) return U96_ERR_INVALID;
     Bank &k = h->bank[bank];
     if (!k.filled || k.from > min_from) return U96_ERR_STATE;
+    if (min_from == FROM_XSBL && !k.has_disp) return U96_ERR_STATE;      // set_rect_image without start: no x-Sobel images yet
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
-    const int W = h->bm.width, H = h->bm.height;
-    (void)frame;
     uint8_t *dst[2] = {L, R};
-    if (!k.pending) { const int rc = ensure_stage(h, k); if (rc != U96_OK) return rc; }
+    if (!k.pending) { const int rc = ensure_stage(h, k, k.W, k.H); if (rc != U96_OK) return rc; }
     for (int i = 0; i < 2; i++)
-        CK(copy2d(dst[i], W, cur[i], pitch, W, (size_t)H * k.n, cudaMemcpyDeviceToHost, s, k.pending ? nullptr : stage_in(h, k, i)));
+        CK(copy2d(dst[i], k.W, cur[i], pitch, k.W, (size_t)k.H * k.n, cudaMemcpyDeviceToHost, s, k.pending ? nullptr : stage_in(h, k, i)));
     CK(cudaStreamSynchronize(s));
     return U96_OK;
 }
+
+// kernel time of an auxiliary call (reproject / keypoints / uvc) when profiling is on
+struct AuxTimer {
+    u96_handle *h; int which; cudaStream_t s; bool on;
+    AuxTimer(u96_handle *h_, int which_, cudaStream_t s_) : h(h_), which(which_), s(s_), on(h_->profiling) { if (on) cudaEventRecord(h->aux_ev[0], s); }
+    void stop() { if (on) cudaEventRecord(h->aux_ev[1], s); }
+    void read()
+    {
+        h->aux_valid[which] = false;
+        if (on && cudaEventElapsedTime(&h->aux_ms[which], h->aux_ev[0], h->aux_ev[1]) == cudaSuccess) h->aux_valid[which] = true;
+    }
+};
 
 extern "C" {
 
@@ -499,6 +576,31 @@ int u96_submit_rect_device(u96_handle *h, int bank, const void *dL, const void *
 int u96_submit_xsbl_device(u96_handle *h, int bank, const void *dL, const void *dR, int stride, int n)
 { return submit_common(h, bank, FROM_XSBL, (const uint8_t *)dL, (const uint8_t *)dR, stride, n, true); }
 
+int u96_set_rect_image(u96_handle *h, int bank, const uint8_t *L, const uint8_t *R, int stride, int n)
+{ return submit_common(h, bank, FROM_RECT, L, R, stride, n, false, nullptr, true); }
+
+int u96_start_xsbl(u96_handle *h, int bank)
+{
+    if (!h || bank < 0 || bank > 1) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (k.pending || !k.filled || k.from != FROM_RECT) return U96_ERR_STATE;
+    if (k.W != h->bm.width || k.H != h->bm.height) return U96_ERR_STATE;      // the geometry changed since set_rect_image
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    { const int rc = ensure_bank_buffers(h, k, FROM_RECT, k.n, false); if (rc != U96_OK) return rc; }
+    k.has_eig = h->gftt;
+    k.staged = false;
+    const bool prof = h->profiling;
+    if (prof) { CKA(cudaEventRecord(k.ev[0], s)); CKA(cudaEventRecord(k.ev[1], s)); }
+    const int rc = run_range(h, k, FROM_RECT, 0, k.n, s, prof);
+    if (rc != U96_OK) return abort_submit(h, k, s, rc);
+    CKA(cudaGetLastError());
+    CKA(cudaEventRecord(k.done, s));
+    k.has_disp = true; k.pending = true;
+    h->fifo.push_back(bank);
+    return U96_OK;
+}
+
 int u96_wait(u96_handle *h, int *active_bank)
 {
     if (!h) return U96_ERR_INVALID;
@@ -516,26 +618,25 @@ int u96_receive_rect(u96_handle *h, int bank, uint8_t *L, uint8_t *R)
 {
     if (!h || bank < 0 || bank > 1) return U96_ERR_INVALID;
     Bank &k = h->bank[bank];
-    return receive_u8(h, bank, k.cur_rect, k.rect_pitch, k.rect_frame, FROM_RECT, L, R);
+    return receive_u8(h, bank, k.cur_rect, k.rect_pitch, FROM_RECT, L, R);
 }
 
 int u96_receive_xsbl(u96_handle *h, int bank, uint8_t *L, uint8_t *R)
 {
     if (!h || bank < 0 || bank > 1) return U96_ERR_INVALID;
     Bank &k = h->bank[bank];
-    return receive_u8(h, bank, k.cur_xsbl, k.xsbl_pitch, k.xsbl_frame, FROM_XSBL, L, R);
+    return receive_u8(h, bank, k.cur_xsbl, k.xsbl_pitch, FROM_XSBL, L, R);
 }
 
 int u96_receive_disp(u96_handle *h, int bank, int16_t *disp)
 {
     if (!h || bank < 0 || bank > 1 || !disp) return U96_ERR_INVALID;
     Bank &k = h->bank[bank];
-    if (!k.filled) return U96_ERR_STATE;
+    if (!k.filled || !k.has_disp) return U96_ERR_STATE;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
-    const int W = h->bm.width, H = h->bm.height;
-    if (!k.pending) { const int rc = ensure_stage(h, k); if (rc != U96_OK) return rc; }
-    CK(copy2d(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
+    if (!k.pending) { const int rc = ensure_stage(h, k, k.W, k.H); if (rc != U96_OK) return rc; }
+    CK(copy2d(disp, (size_t)k.W * 2, k.disp, (size_t)h->pitch * 2, (size_t)k.W * 2, (size_t)k.H * k.n,
                          cudaMemcpyDeviceToHost, s, k.pending ? nullptr : stage_out(h, k)));
     CK(cudaStreamSynchronize(s));
     return U96_OK;
@@ -545,11 +646,10 @@ int u96_receive_eigen(u96_handle *h, int bank, uint16_t *eig, uint16_t *max_eig)
 {
     if (!h || bank < 0 || bank > 1 || !eig) return U96_ERR_INVALID;
     Bank &k = h->bank[bank];
-    if (!k.filled || !k.has_eig) return U96_ERR_STATE;
+    if (!k.filled || !k.has_eig || !k.has_disp) return U96_ERR_STATE;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
-    const int W = h->bm.width, H = h->bm.height;
-    CK(copy2d(eig, (size_t)W * 2, k.eig, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n, cudaMemcpyDeviceToHost, s));
+    CK(copy2d(eig, (size_t)k.W * 2, k.eig, (size_t)h->pitch * 2, (size_t)k.W * 2, (size_t)k.H * k.n, cudaMemcpyDeviceToHost, s));
     std::vector<uint32_t> mx(max_eig ? k.n : 0);
     if (max_eig) CK(cudaMemcpyAsync(mx.data(), k.eig_max, (size_t)k.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -564,32 +664,78 @@ int u96_enqueue_receive_disp(u96_handle *h, int bank, int16_t *disp)
     if (!k.filled || !k.pending) return U96_ERR_STATE;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
-    const int W = h->bm.width, H = h->bm.height;
-    CK(copy2d(disp, (size_t)W * 2, k.disp, (size_t)h->pitch * 2, (size_t)W * 2, (size_t)H * k.n,
+    CK(copy2d(disp, (size_t)k.W * 2, k.disp, (size_t)h->pitch * 2, (size_t)k.W * 2, (size_t)k.H * k.n,
                          cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(k.done, s));                          // wait() now covers the copy as well
     return U96_OK;
 }
 
-int u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_r[12], int decim, int flags, float *xyz)
+// StereoCameraModel.cpp:9-14
+static const float kLocalTransform[12] = {0.0f, 0.0f, 1.0f, 0.0f, -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, -1.0f, 0.0f, 0.0f};
+
+int u96_reproject_ex(u96_handle *h, int bank, const double P_l[12], const double P_r[12], int decim,
+                     const float *local_T, const float *poses, float *xyz)
 {
     if (!h || bank < 0 || bank > 1 || !P_l || !P_r || !xyz) return U96_ERR_INVALID;
     if (decim != 1 && decim != 2 && decim != 4 && decim != 8) return U96_ERR_INVALID;
     Bank &k = h->bank[bank];
-    if (!k.filled) return U96_ERR_STATE;
+    if (!k.filled || !k.has_disp) return U96_ERR_STATE;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
-    const int W = h->bm.width, H = h->bm.height;
-    const size_t count = (size_t)(W / decim) * (H / decim) * k.n * 3;
+    const size_t count = (size_t)(k.W / decim) * (k.H / decim) * k.n * 3;
     if (count > h->xyz_cap) {
         cudaFree(h->xyz); h->xyz = nullptr; h->xyz_cap = 0;
         if (cudaMalloc(&h->xyz, count * sizeof(float)) != cudaSuccess) return U96_ERR_NOMEM;
         h->xyz_cap = count;
     }
-    h->launches += launch_reproject(k.disp, h->pitch, (size_t)h->pitch * H, W, H, k.n, P_l, P_r, decim, flags, h->xyz, s);
+    if (poses) {
+        if (!h->poses && cudaMalloc(&h->poses, (size_t)h->maxB * 12 * sizeof(float)) != cudaSuccess) return U96_ERR_NOMEM;
+        CK(cudaMemcpyAsync(h->poses, poses, (size_t)k.n * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    AuxTimer t(h, U96_AUX_REPROJECT, s);
+    h->launches += launch_reproject(k.disp, h->pitch, (size_t)h->pitch * k.H, k.W, k.H, k.n, P_l, P_r, decim, local_T,
+                                    poses ? h->poses : nullptr, h->xyz, s);
+    t.stop();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(xyz, h->xyz, count * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    t.read();
+    return U96_OK;
+}
+
+int u96_reproject(u96_handle *h, int bank, const double P_l[12], const double P_r[12], int decim, int flags, float *xyz)
+{ return u96_reproject_ex(h, bank, P_l, P_r, decim, (flags & 1) ? kLocalTransform : nullptr, nullptr, xyz); }
+
+int u96_reproject_points(u96_handle *h, int bank, int frame, const double P_l[12], const double P_r[12], const float *uv, int n,
+                         const uint8_t *mask, float min_depth, float max_depth, const float *local_T, float *xyz)
+{
+    if (!h || bank < 0 || bank > 1 || !P_l || !P_r || n < 0 || (n > 0 && (!uv || !xyz))) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!k.filled || !k.has_disp) return U96_ERR_STATE;
+    if (frame < 0 || frame >= k.n) return U96_ERR_INVALID;
+    if (n == 0) return U96_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = bank_stream(h, bank);
+    const size_t need = (size_t)n * 6;                       // floats: uv | xyz | mask bytes (rounded up to n/4 floats + 1)
+    const size_t words = need + (size_t)n / 4 + 1;
+    if (words > h->kp_cap) {
+        cudaFree(h->kp); h->kp = nullptr; h->kp_cap = 0;
+        const size_t cap = std::max(words, (size_t)8192);
+        if (cudaMalloc(&h->kp, cap * sizeof(float)) != cudaSuccess) return U96_ERR_NOMEM;
+        h->kp_cap = cap;
+    }
+    float *d_uv = h->kp, *d_xyz = h->kp + (size_t)2 * n;
+    uint8_t *d_mask = reinterpret_cast<uint8_t *>(h->kp + (size_t)5 * n);
+    CK(cudaMemcpyAsync(d_uv, uv, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (mask) CK(cudaMemcpyAsync(d_mask, mask, (size_t)n, cudaMemcpyHostToDevice, s));
+    AuxTimer t(h, U96_AUX_REPROJECT_POINTS, s);
+    h->launches += launch_reproject_points(k.disp + (size_t)frame * h->pitch * k.H, h->pitch, k.W, k.H, P_l, P_r, d_uv,
+                                           mask ? d_mask : nullptr, n, min_depth, max_depth, local_T, d_xyz, s);
+    t.stop();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(xyz, d_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    t.read();
     return U96_OK;
 }
 
@@ -600,24 +746,28 @@ int u96_receive_uvc(u96_handle *h, int bank, int which, uint8_t *frame)
     Bank &k = h->bank[bank];
     if (!k.filled) return U96_ERR_STATE;
     if ((which == U96_UVC_RECT && k.from > FROM_RECT)) return U96_ERR_STATE;      // the bank holds no rectified images
+    if (which != U96_UVC_RECT && !k.has_disp) return U96_ERR_STATE;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = bank_stream(h, bank);
-    const int W = h->bm.width, H = h->bm.height;
+    const int W = k.W, H = k.H;
     const size_t bytes = (size_t)k.n * H * W * 4;
     if (bytes > h->uvc_cap) {
         cudaFree(h->uvc); h->uvc = nullptr; h->uvc_cap = 0;
         if (cudaMalloc(&h->uvc, bytes) != cudaSuccess) return U96_ERR_NOMEM;
         h->uvc_cap = bytes;
     }
+    AuxTimer t(h, U96_AUX_UVC, s);
     if (which == U96_UVC_BM)
         h->launches += launch_pack_uvc(nullptr, nullptr, 0, 0, k.disp, h->pitch, (size_t)h->pitch * H, h->uvc, W, H, k.n, s);
     else if (which == U96_UVC_RECT)
         h->launches += launch_pack_uvc(k.cur_rect[0], k.cur_rect[1], k.rect_pitch, k.rect_frame, nullptr, 0, 0, h->uvc, W, H, k.n, s);
     else
         h->launches += launch_pack_uvc(k.cur_xsbl[0], k.cur_xsbl[1], k.xsbl_pitch, k.xsbl_frame, nullptr, 0, 0, h->uvc, W, H, k.n, s);
+    t.stop();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(frame, h->uvc, bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    t.read();
     return U96_OK;
 }
 
@@ -625,7 +775,7 @@ int u96_bank_device_ptr(u96_handle *h, int bank, int which, void **dptr, int *pi
 {
     if (!h || bank < 0 || bank > 1 || !dptr || which < 0 || which >= U96_BUF_COUNT) return U96_ERR_INVALID;
     Bank &k = h->bank[bank];
-    const int H = h->bm.height;
+    const int H = k.filled ? k.H : h->bm.height;
     const void *p = nullptr; int pitch = h->pitch; size_t frame = (size_t)h->pitch * H;
     switch (which) {
     case U96_BUF_RAW_L: case U96_BUF_RAW_R: p = k.raw[which - U96_BUF_RAW_L]; break;
@@ -647,18 +797,46 @@ int u96_host_alloc(void **p, size_t bytes)
     return U96_OK;
 }
 
+int u96_host_alloc_wc(void **p, size_t bytes)
+{
+    if (!p) return U96_ERR_INVALID;
+    CK(cudaHostAlloc(p, bytes, cudaHostAllocWriteCombined));
+    return U96_OK;
+}
+
 int u96_host_free(void *p)
 {
     CK(cudaFreeHost(p));
     return U96_OK;
 }
 
+int u96_last_stage_ms_ex(u96_handle *h, int bank, float *ms, int count)
+{
+    if (!h || bank < 0 || bank > 1 || !ms || count < 1 || count > U96_STAGE_COUNT) return U96_ERR_INVALID;
+    Bank &k = h->bank[bank];
+    if (!h->profiling || !k.filled || !k.has_disp || k.pending || k.staged) return U96_ERR_STATE;
+    for (int i = 0; i < count; i++) CK(cudaEventElapsedTime(&ms[i], k.ev[i], k.ev[i + 1]));
+    return U96_OK;
+}
+
 int u96_last_stage_ms(u96_handle *h, int bank, float ms[4])
 {
-    if (!h || bank < 0 || bank > 1 || !ms) return U96_ERR_INVALID;
-    Bank &k = h->bank[bank];
-    if (!h->profiling || !k.filled || k.pending) return U96_ERR_STATE;
-    for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms[i], k.ev[i], k.ev[i + 1]));
+    if (!ms) return U96_ERR_INVALID;
+    float v[U96_STAGE_COUNT];
+    const int rc = u96_last_stage_ms_ex(h, bank, v, U96_STAGE_COUNT);
+    if (rc != U96_OK) return rc;
+    ms[0] = v[U96_STAGE_H2D];
+    ms[1] = v[U96_STAGE_RECT] + v[U96_STAGE_GFTT];
+    ms[2] = v[U96_STAGE_XSBL];
+    ms[3] = v[U96_STAGE_BM] + v[U96_STAGE_POST];
+    return U96_OK;
+}
+
+int u96_last_aux_ms(u96_handle *h, int which, float *ms)
+{
+    if (!h || !ms || which < 0 || which >= U96_AUX_COUNT) return U96_ERR_INVALID;
+    if (!h->aux_valid[which]) return U96_ERR_STATE;
+    *ms = h->aux_ms[which];
     return U96_OK;
 }
 

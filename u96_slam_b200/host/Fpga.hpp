@@ -64,18 +64,17 @@ public:
                                     ((uint32_t)enable << 31) | ((uint32_t)(mode & 1) << 16) | (uint32_t)(thr & 0x3FF)) == U96_OK ? 0 : -1;
     }
 
-    // FPGA.cpp:236-249 -- copies the rectified pair into the RECT bank
-    void setRectImage(int bank, const Mat8 &imageLeft, const Mat8 &imageRight)
+    // FPGA.cpp:236-249 -- copies the rectified pair into the RECT bank, at call time like the reference's memcpy:
+    // receiveRectImages(bank) right after it reads the pair back, and the caller's images may be reused at once.
+    // (void in the reference; the status is returned here because nothing in this library exits or spins.)
+    int setRectImage(int bank, const Mat8 &imageLeft, const Mat8 &imageRight)
     {
-        staged_[bank & 1][0] = imageLeft; staged_[bank & 1][1] = imageRight;
+        if (imageLeft.empty() || imageRight.empty() || imageLeft.cols != IMAGE_WIDTH || imageLeft.rows != IMAGE_HEIGHT ||
+            imageRight.cols != IMAGE_WIDTH || imageRight.rows != IMAGE_HEIGHT) return -1;
+        return u96_set_rect_image(h_, bank, imageLeft.data.data(), imageRight.data.data(), IMAGE_WIDTH, 1) == U96_OK ? 0 : -1;
     }
-    // main.cpp:172-174 FPGA_XSBL_SW_START: xsbl -> bm on the staged pair
-    int startXsbl(int bank)
-    {
-        const Mat8 &L = staged_[bank & 1][0], &R = staged_[bank & 1][1];
-        if (L.empty() || R.empty() || L.cols != IMAGE_WIDTH || L.rows != IMAGE_HEIGHT) return -1;
-        return u96_submit_rect(h_, bank, L.data.data(), R.data.data(), L.cols, 1) == U96_OK ? 0 : -1;
-    }
+    // main.cpp:172-174 `reg->xsbl.Control |= FPGA_XSBL_SW_START`: xsbl -> bm on what the RECT bank holds
+    int startXsbl(int bank) { return u96_start_xsbl(h_, bank) == U96_OK ? 0 : -1; }
     // sensor path (CameraStereoImages.cpp:134-149): raw pair -> rect -> xsbl -> bm
     int captureRaw(int bank, const Mat8 &rawLeft, const Mat8 &rawRight)
     {
@@ -126,12 +125,22 @@ public:
         xyz.resize((size_t)(IMAGE_HEIGHT / decim) * (IMAGE_WIDTH / decim) * 3);
         return u96_reproject(h_, bank, P_l, P_r, decim, localTransform ? 1 : 0, xyz.data()) == U96_OK ? 0 : -1;
     }
+    // generateKeypoints3D (Stereo.cpp:119-154, called per frame at main.cpp:250-252) with DEPTH_METHOD_FPGA_BM: keypoints =
+    // n (x, y) float pairs in the left rectified image -> n (X, Y, Z) in the body frame (localTransform applied), NaN = bad
+    // point; minDepth = maxDepth = 0 like the reference's call
+    int generateKeypoints3D(int bank, const double P_l[12], const double P_r[12], const std::vector<float> &keypoints,
+                            std::vector<float> &kpts3d, float minDepth = 0.0f, float maxDepth = 0.0f)
+    {
+        static const float local[12] = {0.f, 0.f, 1.f, 0.f, -1.f, 0.f, 0.f, 0.f, 0.f, -1.f, 0.f, 0.f};   // StereoCameraModel.cpp:9-14
+        const int n = (int)(keypoints.size() / 2);
+        kpts3d.resize((size_t)n * 3);
+        return u96_reproject_points(h_, bank, 0, P_l, P_r, keypoints.data(), n, nullptr, minDepth, maxDepth, local, kpts3d.data()) == U96_OK ? 0 : -1;
+    }
     u96_handle *handle() { return h_; }
 
 private:
     int device_;
     u96_handle *h_ = nullptr;
-    Mat8 staged_[2][2];
 };
 
 }  // namespace u96

@@ -29,9 +29,14 @@ int main(int argc, char **argv)
                 if (x >= 12) R.data[(size_t)y * 640 + x - 12] = v;
             }
         const int bank = it % 2;                                        // main.cpp:168
-        fpga.setRectImage(bank, L, R);
-        if (fpga.startXsbl(bank) != 0) return 3;
+        if (fpga.setRectImage(bank, L, R) != 0) return 8;
+        // the reference's setRectImage writes the bank (FPGA.cpp:236-249): the pair reads back before anything has run,
+        // the disparity of this bank does not exist yet
         u96::Mat8 rl, rr; u96::Mat16 depth;
+        if (fpga.receiveRectImages(bank, rl, rr) != 0 || rl.data != L.data || rr.data != R.data) return 9;
+        if (it < 2 && fpga.receiveDepthMap(bank, depth) == 0) return 10;
+        L.data.assign(L.data.size(), 0);                                  // the caller's images are free again
+        if (fpga.startXsbl(bank) != 0) return 3;
         const int active = fpga.receiveData(rl, rr, depth);
         if (active != bank) return 4;
         const u96::Mat16 small = u96::decimateDisparity(depth, 4);     // SensorData.cpp:50-58
@@ -46,6 +51,19 @@ int main(int argc, char **argv)
         const double thr = maxEigen * 0.01;
         int cand = 0;
         for (int y = 1; y < 479; y++) for (int x = 1; x < 639; x++) cand += ((float)eig[(size_t)y * 640 + x] >= thr);
+        // generateKeypoints3D (main.cpp:250-252): every 7th candidate as a keypoint at a sub-pixel position
+        std::vector<float> kp, kp3;
+        for (int y = 1, c = 0; y < 479; y++) for (int x = 1; x < 639; x++)
+            if ((float)eig[(size_t)y * 640 + x] >= thr && (c++ % 7) == 0) { kp.push_back(x + 0.25f); kp.push_back(y + 0.5f); }
+        if (fpga.generateKeypoints3D(active, P_l, P_r, kp, kp3) != 0) return 11;
+        int kp_ok = 0, kp_match = 0;
+        for (size_t i = 0; i < kp.size() / 2; i++) {
+            const short s = depth.at((int)kp[2 * i + 1], (int)kp[2 * i]);
+            const bool good = kp3[3 * i] == kp3[3 * i];
+            kp_ok += good;
+            kp_match += (good == (s > 0));                                // a point exists exactly where the map holds a positive disparity
+        }
+        printf("kpts3d %d of %d consistent %d ; ", kp_ok, (int)(kp.size() / 2), kp_match);
         printf("frame %d bank %d valid %lld mean_disp %.3f frac_at_12px %.3f decimated %dx%d eig_max %u candidates %d points %d\n", it, active,
                valid, valid ? sum / 16.0 / valid : 0.0, valid ? (double)at12 / valid : 0.0, small.cols, small.rows, (unsigned)maxEigen, cand, pts);
     }

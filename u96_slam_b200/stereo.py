@@ -20,6 +20,9 @@ PROFILE_RTL, PROFILE_OPENCV = 0, 1
 UVC_RECT, UVC_XSBL, UVC_BM = 1, 2, 3
 BUF_RAW_L, BUF_RAW_R, BUF_RECT_L, BUF_RECT_R, BUF_XSBL_L, BUF_XSBL_R, BUF_DISP = range(7)
 
+# StereoCameraModel's localTransform (slam/src/core/StereoCameraModel.cpp:9-14): z-forward camera -> x-forward body
+LOCAL_TRANSFORM = np.array([0, 0, 1, 0, -1, 0, 0, 0, 0, -1, 0, 0], np.float32)
+
 # shipped rectification parameter set (StereoBM/src/fpga.c:190-226)
 SHIPPED_RECT_PARAMS = dict(
     f=[[40419817, 40382910], [39609530, 39627967]], c=[320, 240],
@@ -98,6 +101,15 @@ def load_library():
     L.u96_receive_eigen.argtypes = [vp, i32, vp, vp]
     L.u96_enqueue_receive_disp.argtypes = [vp, i32, vp]
     L.u96_reproject.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), i32, i32, vp]
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.u96_reproject_ex.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), i32, fp, fp, vp]
+    L.u96_reproject_points.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp, i32, vp,
+                                       ctypes.c_float, ctypes.c_float, fp, vp]
+    L.u96_set_rect_image.argtypes = [vp, i32, u8p, u8p, i32, i32]
+    L.u96_start_xsbl.argtypes = [vp, i32]
+    L.u96_host_alloc_wc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.u96_last_stage_ms_ex.argtypes = [vp, i32, fp, i32]
+    L.u96_last_aux_ms.argtypes = [vp, i32, fp]
     L.u96_bank_device_ptr.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_size_t)]
     L.u96_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.u96_host_free.argtypes = [vp]
@@ -138,6 +150,9 @@ class StereoFrontEnd:
         _check(self.L, self.L.u96_create(ctypes.byref(self.h), device, max_w, max_h, max_batch), "u96_create")
         self.device, self.max_batch = device, max_batch
         self._n = [0, 0]
+        self._geom = [None, None]                       # (W, H) each bank was filled with
+        p = self.get_bm_params()                        # the handle starts with the firmware's defaults (fpga.c:150-160)
+        self.W, self.H = p["width"], p["height"]
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -189,7 +204,15 @@ class StereoFrontEnd:
         if (W, H) != (self.W, self.H):
             raise ValueError(f"image {W}x{H} != configured {self.W}x{self.H}")
         _check(self.L, fn(self.h, bank, L.ctypes.data, R.ctypes.data, W, n), fn.__name__)
-        self._n[bank] = n
+        self._n[bank] = n; self._geom[bank] = (self.W, self.H)
+
+    def set_rect_image(self, bank, L, R):
+        """Fpga::setRectImage (FPGA.cpp:236-249): write the pair(s) into the RECT bank, run nothing"""
+        self._submit(self.L.u96_set_rect_image, bank, L, R)
+
+    def start_xsbl(self, bank):
+        """reg->xsbl.Control |= FPGA_XSBL_SW_START (main.cpp:172-174)"""
+        _check(self.L, self.L.u96_start_xsbl(self.h, bank), "u96_start_xsbl")
 
     def submit_raw(self, bank, L, R):
         self._submit(self.L.u96_submit_raw, bank, L, R)
@@ -204,18 +227,18 @@ class StereoFrontEnd:
         fn = {"raw": self.L.u96_submit_raw_device, "rect": self.L.u96_submit_rect_device,
               "xsbl": self.L.u96_submit_xsbl_device}[kind]
         _check(self.L, fn(self.h, bank, ctypes.c_void_p(dptr_l), ctypes.c_void_p(dptr_r), stride, n), fn.__name__)
-        self._n[bank] = n
+        self._n[bank] = n; self._geom[bank] = (self.W, self.H)
 
     def submit_host_ptr(self, kind, bank, ptr_l, ptr_r, stride, n):
         fn = {"raw": self.L.u96_submit_raw, "rect": self.L.u96_submit_rect, "xsbl": self.L.u96_submit_xsbl}[kind]
         _check(self.L, fn(self.h, bank, ctypes.c_void_p(ptr_l), ctypes.c_void_p(ptr_r), stride, n), fn.__name__)
-        self._n[bank] = n
+        self._n[bank] = n; self._geom[bank] = (self.W, self.H)
 
     def submit_host_ptr_async(self, kind, bank, ptr_l, ptr_r, stride, n, disp_out_ptr):
         """pipelined submit: H2D, kernels and the D2H of the disparity overlap chunk by chunk"""
         fn = {"raw": self.L.u96_submit_raw_async, "rect": self.L.u96_submit_rect_async}[kind]
         _check(self.L, fn(self.h, bank, ctypes.c_void_p(ptr_l), ctypes.c_void_p(ptr_r), stride, n, ctypes.c_void_p(disp_out_ptr)), fn.__name__)
-        self._n[bank] = n
+        self._n[bank] = n; self._geom[bank] = (self.W, self.H)
 
     def wait(self):
         b = ctypes.c_int(-1)
@@ -223,8 +246,8 @@ class StereoFrontEnd:
         return b.value
 
     def _recv_pair(self, fn, bank):
-        n = self._n[bank]
-        L = np.empty((n, self.H, self.W), np.uint8); R = np.empty_like(L)
+        n = self._n[bank]; W, H = self._geom[bank]
+        L = np.empty((n, H, W), np.uint8); R = np.empty_like(L)
         _check(self.L, fn(self.h, bank, L.ctypes.data, R.ctypes.data), fn.__name__)
         return L, R
 
@@ -235,8 +258,8 @@ class StereoFrontEnd:
         return self._recv_pair(self.L.u96_receive_xsbl, bank)
 
     def receive_disp(self, bank, out=None):
-        n = self._n[bank]
-        d = out if out is not None else np.empty((n, self.H, self.W), np.int16)
+        n = self._n[bank]; W, H = self._geom[bank]
+        d = out if out is not None else np.empty((n, H, W), np.int16)
         _check(self.L, self.L.u96_receive_disp(self.h, bank, d.ctypes.data), "u96_receive_disp")
         return d
 
@@ -246,15 +269,15 @@ class StereoFrontEnd:
 
     def receive_eigen(self, bank):
         """Fpga::receiveEigen (FPGA.cpp:281-296): (n, H, W) u16 min-eigenvalue map, (n,) u16 per-frame maxima (gftt.Max)"""
-        n = self._n[bank]
-        e = np.empty((n, self.H, self.W), np.uint16); m = np.empty(n, np.uint16)
+        n = self._n[bank]; W, H = self._geom[bank]
+        e = np.empty((n, H, W), np.uint16); m = np.empty(n, np.uint16)
         _check(self.L, self.L.u96_receive_eigen(self.h, bank, e.ctypes.data, m.ctypes.data), "u96_receive_eigen")
         return e, m
 
     def receive_uvc(self, bank, which):
         """UVC payload of the firmware (xusb_main.c:293-376): (n, H, 2W, 2) u8 YUYV; which = UVC_RECT / UVC_XSBL / UVC_BM"""
-        n = self._n[bank]
-        f = np.empty((n, self.H, 2 * self.W, 2), np.uint8)
+        n = self._n[bank]; W, H = self._geom[bank]
+        f = np.empty((n, H, 2 * W, 2), np.uint8)
         _check(self.L, self.L.u96_receive_uvc(self.h, bank, which, f.ctypes.data), "u96_receive_uvc")
         return f
 
@@ -268,10 +291,39 @@ class StereoFrontEnd:
     def reproject(self, bank, P_l, P_r, decim=1, apply_local=False):
         n = self._n[bank]
         Pl = np.ascontiguousarray(P_l, np.float64).reshape(12); Pr = np.ascontiguousarray(P_r, np.float64).reshape(12)
-        out = np.empty((n, self.H // decim, self.W // decim, 3), np.float32)
+        W, H = self._geom[bank]
+        out = np.empty((n, H // decim, W // decim, 3), np.float32)
         dp = ctypes.POINTER(ctypes.c_double)
         _check(self.L, self.L.u96_reproject(self.h, bank, Pl.ctypes.data_as(dp), Pr.ctypes.data_as(dp), decim,
                                             1 if apply_local else 0, out.ctypes.data), "u96_reproject")
+        return out
+
+    def reproject_ex(self, bank, P_l, P_r, decim=1, local_T=None, poses=None):
+        """dense consumer of main.cpp:522-551: local_T 12 floats or None, poses (n, 12) floats or None"""
+        n = self._n[bank]
+        Pl = np.ascontiguousarray(P_l, np.float64).reshape(12); Pr = np.ascontiguousarray(P_r, np.float64).reshape(12)
+        W, H = self._geom[bank]
+        out = np.empty((n, H // decim, W // decim, 3), np.float32)
+        dp, fp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)
+        lt = None if local_T is None else np.ascontiguousarray(local_T, np.float32).reshape(12)
+        ps = None if poses is None else np.ascontiguousarray(poses, np.float32).reshape(n, 12)
+        _check(self.L, self.L.u96_reproject_ex(self.h, bank, Pl.ctypes.data_as(dp), Pr.ctypes.data_as(dp), decim,
+                                               None if lt is None else lt.ctypes.data_as(fp), None if ps is None else ps.ctypes.data_as(fp),
+                                               out.ctypes.data), "u96_reproject_ex")
+        return out
+
+    def reproject_points(self, bank, P_l, P_r, uv, frame=0, min_depth=0.0, max_depth=0.0, local_T=LOCAL_TRANSFORM, mask=None):
+        """generateKeypoints3DStereo (Stereo.cpp:53-117): uv (n, 2) float32 keypoints (x, y) -> (n, 3) float32, NaN = bad point"""
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        n = uv.shape[0]
+        Pl = np.ascontiguousarray(P_l, np.float64).reshape(12); Pr = np.ascontiguousarray(P_r, np.float64).reshape(12)
+        out = np.empty((n, 3), np.float32)
+        dp, fp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)
+        lt = None if local_T is None else np.ascontiguousarray(local_T, np.float32).reshape(12)
+        mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        _check(self.L, self.L.u96_reproject_points(self.h, bank, frame, Pl.ctypes.data_as(dp), Pr.ctypes.data_as(dp), uv.ctypes.data, n,
+                                                   None if mk is None else mk.ctypes.data, min_depth, max_depth,
+                                                   None if lt is None else lt.ctypes.data_as(fp), out.ctypes.data), "u96_reproject_points")
         return out
 
     def bank_device_ptr(self, bank, which):
@@ -285,10 +337,10 @@ class StereoFrontEnd:
         send buffer of the optional multi-GPU gather; valid until the bank is submitted again."""
         import torch
         ptr, pitch, frame = self.bank_device_ptr(bank, BUF_DISP)
-        n = self._n[bank]
+        n = self._n[bank]; W, H = self._geom[bank]
 
         class _Cai:                                    # CUDA array interface v2
-            __cuda_array_interface__ = {"shape": (n, self.H, self.W), "typestr": "<i2", "data": (ptr, False), "version": 2,
+            __cuda_array_interface__ = {"shape": (n, H, W), "typestr": "<i2", "data": (ptr, False), "version": 2,
                                         "strides": (frame, pitch, 2)}
         return torch.as_tensor(_Cai(), device=f"cuda:{self.device}")
 
@@ -296,6 +348,17 @@ class StereoFrontEnd:
         ms = (ctypes.c_float * 4)()
         _check(self.L, self.L.u96_last_stage_ms(self.h, bank, ms), "u96_last_stage_ms")
         return dict(zip(("h2d", "rect", "xsbl", "bm"), list(ms)))
+
+    def last_stage_ms_ex(self, bank):
+        ms = (ctypes.c_float * 6)()
+        _check(self.L, self.L.u96_last_stage_ms_ex(self.h, bank, ms, 6), "u96_last_stage_ms_ex")
+        return dict(zip(("h2d", "rect", "gftt", "xsbl", "bm", "post"), list(ms)))
+
+    def last_aux_ms(self, which):
+        """kernel ms of the last reproject (0) / reproject_points (1) / receive_uvc (2) call; needs set_profiling"""
+        v = ctypes.c_float()
+        _check(self.L, self.L.u96_last_aux_ms(self.h, which, ctypes.byref(v)), "u96_last_aux_ms")
+        return v.value
 
     def kernel_launches(self):
         return int(self.L.u96_kernel_launches(self.h))
@@ -321,7 +384,6 @@ class Fpga:
     def __init__(self, device=0, width=640, height=480):
         self.device, self.IMAGE_WIDTH, self.IMAGE_HEIGHT = device, width, height
         self.fe = None
-        self._staged = {}
 
     def registerOpen(self):
         try:
@@ -342,12 +404,16 @@ class Fpga:
     memoryClose = lambda self: 0
 
     def setRectImage(self, bank, imageLeft, imageRight):
-        self._staged[bank] = (np.ascontiguousarray(imageLeft, np.uint8), np.ascontiguousarray(imageRight, np.uint8))
+        """FPGA.cpp:236-249: the pair is written into the RECT bank at call time"""
+        self.fe.set_rect_image(bank, imageLeft, imageRight)
 
     def start(self, bank):
-        """FPGA_XSBL_SW_START: run xsbl -> bm on the staged rectified pair."""
-        L, R = self._staged.pop(bank)
-        self.fe.submit_rect(bank, L, R)
+        """FPGA_XSBL_SW_START: run xsbl -> bm on the RECT bank."""
+        self.fe.start_xsbl(bank)
+
+    def generateKeypoints3D(self, bank, P_l, P_r, keypoints, minDepth=0.0, maxDepth=0.0):
+        """Stereo.cpp:119-154 with DEPTH_METHOD_FPGA_BM: keypoints (n, 2) float32 (x, y) -> (n, 3) float32 in the body frame"""
+        return self.fe.reproject_points(bank, P_l, P_r, keypoints, 0, minDepth, maxDepth)
 
     def captureFromSensor(self, bank, rawLeft, rawRight):
         """sensor path: rect -> xsbl -> bm (CameraStereoImages.cpp:134-149)"""
