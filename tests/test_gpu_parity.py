@@ -142,12 +142,15 @@ def test_c3_kitti_shape_both_profiles(u, oracle, B):
         fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=B, num_disparities=D, x_store_offset=1)
         fe.submit_raw(0, L, R); b = fe.wait()
         gl, gr = fe.receive_rect(b); d = fe.receive_disp(b)
-        wl, wr = oracle.rectify(L[1], rp, 0), oracle.rectify(R[1], rp, 1)
-        assert np.array_equal(gl[1], wl) and np.array_equal(gr[1], wr)
-        assert np.array_equal(d[1], oracle.bm_rtl(oracle.xsobel_rtl(wl), oracle.xsobel_rtl(wr), wsz=B, ndisp=D))
+        for i in range(2):                                           # every frame of the batch
+            wl, wr = oracle.rectify(L[i], rp, 0), oracle.rectify(R[i], rp, 1)
+            assert np.array_equal(gl[i], wl) and np.array_equal(gr[i], wr)
+            assert np.array_equal(d[i], oracle.bm_rtl(oracle.xsobel_rtl(wl), oracle.xsobel_rtl(wr), wsz=B, ndisp=D, bitserial_div=0))
         fe.set_bm_params(profile=u.PROFILE_OPENCV, texture_threshold=10, uniqueness_ratio=10, prefilter_cap=31)
         fe.submit_rect(1, L, R); b = fe.wait()
-        assert np.array_equal(fe.receive_disp(b)[0], oracle.bm_cv(oracle.xsobel_cv(L[0]), oracle.xsobel_cv(R[0]), wsz=B, ndisp=D))
+        d = fe.receive_disp(b)
+        for i in range(2):
+            assert np.array_equal(d[i], oracle.bm_cv(oracle.xsobel_cv(L[i]), oracle.xsobel_cv(R[i]), wsz=B, ndisp=D))
 
 
 def test_c4_full_hd_256_disparities(u, oracle):
@@ -157,12 +160,72 @@ def test_c4_full_hd_256_disparities(u, oracle):
         fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=21, num_disparities=D, rtl_extended=1, x_store_offset=1)
         fe.submit_rect(0, L, R); b = fe.wait()
         d = fe.receive_disp(b)
-        want = oracle.bm_rtl(oracle.xsobel_rtl(L[1]), oracle.xsobel_rtl(R[1]), wsz=21, ndisp=D, rtl_extended=1)
-        assert np.array_equal(d[1], want)
+        for i in range(2):                                           # every frame of the batch
+            want = oracle.bm_rtl(oracle.xsobel_rtl(L[i]), oracle.xsobel_rtl(R[i]), wsz=21, ndisp=D, rtl_extended=1, bitserial_div=0)
+            assert np.array_equal(d[i], want)
         # size-independent properties at full size: borders invalid, range, idempotence, batch == single
         assert (d[:, :10] == -1).all() and (d[:, :, :D + 11] == -1).all() and d.max() < D * 16 + 8
         fe.submit_rect(1, L[1:], R[1:]); b = fe.wait()
         assert np.array_equal(fe.receive_disp(b)[0], d[1])
+
+
+def rotated_rect_params(u, W, H, deg=1.2):
+    """A rectifying rotation of about `deg` degrees about every axis per camera (opposite signs left / right) through the
+    calibration -> 27 registers generator (formats.rect_params_from_calibration)."""
+    def rot(ax, ay, az):
+        cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return Rz @ Ry @ Rx
+    a = np.deg2rad(deg)
+    f = 0.9 * W
+    K_src = [(f * 1.01, f * 1.012, W / 2 + 3, H / 2 - 2), (f * 0.995, f * 0.993, W / 2 - 4, H / 2 + 1)]
+    R_rect = [rot(0.4 * a, a, -0.7 * a), rot(-0.3 * a, -0.8 * a, 0.6 * a)]
+    return u.rect_params_from_calibration(K_src, R_rect, (f * 0.97, f * 0.97, W / 2, H / 2))
+
+
+@pytest.mark.parametrize("kind", ["identity", "rotated"])
+def test_c4_full_hd_raw_path(u, oracle, kind):
+    """the raw entry point at 1920x1080 (k_rect_remap_tma + staged transfers + cluster BM), every frame checked:
+    RECT and DISP banks against the oracle for a near-identity and a rotated rectification set."""
+    W, H, D = 1920, 1080, 256
+    L, R = u.synth_batch(3, 4, 2, W, H, D)
+    rp = u.identity_rect_params(W, H, float(W)) if kind == "identity" else rotated_rect_params(u, W, H)
+    with u.StereoFrontEnd(0, W, H, 2) as fe:
+        fe.set_rect_params(rp)
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=21, num_disparities=D, rtl_extended=1, x_store_offset=1)
+        fe.submit_raw(0, L, R); b = fe.wait()
+        gl, gr = fe.receive_rect(b); xl, xr = fe.receive_xsbl(b); d = fe.receive_disp(b)
+        for i in range(2):
+            wl, wr = oracle.rectify(L[i], rp, 0), oracle.rectify(R[i], rp, 1)
+            assert np.array_equal(gl[i], wl) and np.array_equal(gr[i], wr), (kind, i)
+            sl, sr = oracle.xsobel_rtl(wl), oracle.xsobel_rtl(wr)
+            assert np.array_equal(xl[i], sl) and np.array_equal(xr[i], sr)
+            assert np.array_equal(d[i], oracle.bm_rtl(sl, sr, wsz=21, ndisp=D, rtl_extended=1, bitserial_div=0)), (kind, i)
+        if kind == "rotated":
+            assert (gl[0] != L[0]).mean() > 0.5                      # the map really moves pixels
+            assert (d[0] > 0).mean() > 0.3
+
+
+def test_c4_full_hd_opencv_profile_256_disparities(u, oracle):
+    """VERDICT r1: PROFILE_OPENCV above 1242 px: 1920x1080, D256 (4-CTA clusters), texture + uniqueness, every frame checked;
+    then the main.cpp:210-212 post filters on the same frames."""
+    W, H, D = 1920, 1080, 256
+    L, R = u.synth_batch(3, 8, 2, W, H, D)
+    with u.StereoFrontEnd(0, W, H, 2) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_OPENCV, block_size=21, num_disparities=D, prefilter_cap=31,
+                         texture_threshold=10, uniqueness_ratio=10, disp12_max_diff=-1, speckle_window_size=0, speckle_range=0)
+        fe.submit_rect(0, L, R); b = fe.wait()
+        d = fe.receive_disp(b)
+        for i in range(2):
+            assert np.array_equal(d[i], oracle.bm_cv(oracle.xsobel_cv(L[i]), oracle.xsobel_cv(R[i]), wsz=21, ndisp=D)), i
+        assert (d[0] >= 0).mean() > 0.3
+        fe.set_bm_params(disp12_max_diff=1, speckle_window_size=50, speckle_range=32)
+        fe.submit_rect(1, L, R); b = fe.wait()
+        d2 = fe.receive_disp(b)
+        want = oracle.bm_cv_post(oracle.xsobel_cv(L[1]), oracle.xsobel_cv(R[1]), wsz=21, ndisp=D)
+        assert np.array_equal(d2[1], want)
+        assert (d2[1] != d[1]).sum() > 100                           # the filters did something
 
 
 def test_property_uniform_shift_of_right_image(u, fe640, oracle):

@@ -132,6 +132,57 @@ def test_bm_rtl_cross_check_with_survey(oracle, golden, wsz, uni, thr, valid, to
     assert np.array_equal(d, d2)
 
 
+def _rtl_bm_inputs(kind, W, H, D, seed):
+    import u96_slam_b200 as u
+    from oracle_py import Oracle
+    rng = np.random.default_rng(seed)
+    if kind == "synth":                                              # textured pair with a block-wise disparity field
+        L, R = u.synth_pair(seed, 1, W, H, D)
+        o = Oracle()
+        return o.xsobel_rtl(L), o.xsobel_rtl(R)
+    if kind == "flat":                                               # low-amplitude noise: ties, adjacent minima, zero SADs, guard-lane wins
+        base = rng.integers(30, 34, (H, W + D)).astype(np.uint8)
+        return np.ascontiguousarray(base[:, D:]), np.ascontiguousarray(base[:, D - 3:W + D - 3] ^ (rng.random((H, W)) < 0.02))
+    # saturating: full-swing 6-bit noise (column sums hit 1023 at wsz 21) with a flat band
+    a = rng.integers(0, 64, (H, W)).astype(np.uint8); b = rng.integers(0, 64, (H, W)).astype(np.uint8)
+    a[H // 4:3 * H // 4] = 63; b[H // 4:3 * H // 4] = 0
+    return a, b
+
+
+@pytest.mark.parametrize("D,W,H", [(64, 200, 70), (128, 300, 60), (256, 420, 56), (32, 120, 50), (96, 240, 48), (160, 300, 48)])
+@pytest.mark.parametrize("wsz", [5, 15, 21])
+def test_bm_rtl_oracle_agrees_with_independent_numpy_reading(oracle, D, W, H, wsz):
+    """a6-a14 beyond D = 64 rest on more than one reader.  tests/rtl_bm_numpy.py was written from the
+    Verilog alone; it must equal the C oracle for every dphase count 1..8, uniqueness off / on in both modes, both store
+    offsets and both output extensions, on textured, tie-heavy and saturating inputs."""
+    from rtl_bm_numpy import bm_rtl_numpy
+    n_uni = 0
+    for kind in ("synth", "flat", "sat"):
+        xl, xr = _rtl_bm_inputs(kind, W, H, D, 100 + D + wsz)
+        for (enb, mode, thr, xo, ext) in ((0, 0, 0, 1, 0), (1, 0, 921, 1, int(D > 128)), (1, 1, 600, 0, 1), (1, 0, 0, 1, 1)):
+            want = oracle.bm_rtl(xl, xr, wsz=wsz, ndisp=D, uni_enb=enb, uni_mode=mode, uni_thr=thr, x_store_offset=xo, rtl_extended=ext)
+            got = bm_rtl_numpy(xl, xr, wsz, D, enb, mode, thr, xo, ext)
+            assert np.array_equal(got, want), (kind, enb, mode, thr, xo, ext, int((got != want).sum()))
+            if enb and kind == "synth":
+                off = oracle.bm_rtl(xl, xr, wsz=wsz, ndisp=D, x_store_offset=xo, rtl_extended=ext)
+                n_uni += int((off != want).sum())
+        if kind == "sat" and wsz == 21:
+            assert oracle.sat_events() > 0                           # the 10-bit ceiling really was hit
+    assert n_uni > 0                                                 # the uniqueness filter really changed pixels
+
+
+def test_bm_rtl_independent_reading_on_the_bundled_pair_all_ranges(oracle, golden):
+    """The same cross-check on the reference's own ref_xsbl images at D = 64 / 128 / 256, wsz 15 / 21."""
+    from rtl_bm_numpy import bm_rtl_numpy
+    xl, xr = golden["xsbl_l"][100:260], golden["xsbl_r"][100:260]    # a 160-row band keeps the CPU suite short
+    for D in (64, 128, 256):
+        for wsz in (15, 21):
+            for (enb, thr) in ((0, 0), (1, 921)):
+                want = oracle.bm_rtl(xl, xr, wsz=wsz, ndisp=D, uni_enb=enb, uni_thr=thr, rtl_extended=1)
+                assert np.array_equal(bm_rtl_numpy(xl, xr, wsz, D, enb, 0, thr, 1, 1), want), (D, wsz, enb)
+                assert (want >= 0).mean() > 0.05
+
+
 def test_bm_rtl_saturation_facts(oracle, golden):
     # SURVEY fact 5: 10-bit column-sum saturation happens on ref_xsbl at wsz 21, never at wsz <= 16
     oracle.bm_rtl(golden["xsbl_l"], golden["xsbl_r"], wsz=21, ndisp=64)

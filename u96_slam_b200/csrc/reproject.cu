@@ -15,6 +15,10 @@
 
 namespace u96 {
 
+// std::numeric_limits<float>::quiet_NaN() of the reference's hosts (x86-64, AArch64): 0x7FC00000.  CUDA's CUDART_NAN_F is 0x7FFFFFFF;
+// the bad-point marker is kept bit-identical to the reference's.
+#define U96_QNAN __int_as_float(0x7FC00000)
+
 struct ReprojConst {
     double cx_l, cy_l, fx_l;
     double nx, ny;        // Tx_l/fx_l - Tx_r/fx_r ; Tx_l/fy_l - Tx_r/fy_r   (IEEE double, host computed)
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(256) k_reproject(const int16_t *__restrict__ d
     const size_t base = (size_t)blockIdx.x * 256;
     const size_t idx = base + threadIdx.x;
     const size_t per = (size_t)ow * oh, total = per * n;
-    float X = CUDART_NAN_F, Y = CUDART_NAN_F, Z = CUDART_NAN_F;
+    float X = U96_QNAN, Y = U96_QNAN, Z = U96_QNAN;
     if (idx < total) {
         const int f = (int)(idx / per);
         const int rem = (int)(idx - (size_t)f * per);
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(256) k_reproject(const int16_t *__restrict__ d
                         for (int i = 0; i < 12; i++) p[i] = __ldg(poses + (size_t)f * 12 + i);
                         transform_point(p, X, Y, Z);
                     }
-                } else { X = Y = Z = CUDART_NAN_F; }              // the consumer drops non-finite points
+                } else { X = Y = Z = U96_QNAN; }              // the consumer drops non-finite points
             }
         }
     }
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(128) k_reproject_points(const int16_t *__restr
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float X = CUDART_NAN_F, Y = CUDART_NAN_F, Z = CUDART_NAN_F;
+    float X = U96_QNAN, Y = U96_QNAN, Z = U96_QNAN;
     const float2 p = uv[i];
     // a keypoint outside the map is undefined behaviour in the reference (cv::Mat::at without a check): bad point here
     if ((!mask || mask[i]) && p.x > -1.0f && p.x < (float)W && p.y > -1.0f && p.y < (float)H) {
