@@ -212,14 +212,16 @@ __global__ void __launch_bounds__(128, 8) k_rect_remap(const uint8_t *__restrict
 // image = the "taps outside the source read 0" rule), 8 consumer warps interpolate out of shared
 // memory with the same word/dp4a arithmetic as above and write 128-byte row segments.  HBM sees each
 // source byte once (neighbouring tiles' halo overlap is absorbed by L2) and each destination byte once.
-constexpr int RT_TW = 128, RT_TH = 16, RT_STAGES = 4, RT_CONS = 256, RT_THREADS = RT_CONS + 32, RT_G = RT_TH / 8;
+constexpr int RT_TW = 128, RT_TH = 16, RT_CONS = 256, RT_THREADS = RT_CONS + 32, RT_G = RT_TH / 8;
 
 __global__ void __launch_bounds__(256) k_rect_tile_bbox(const int2 *__restrict__ map, int4 *__restrict__ tiles, int W, int H, int tiles_x, int ntiles)
 {
     __shared__ int s_mm[4];
+    __shared__ int s_row[RT_TH][2];      // per destination row of the tile: min / max source row
     const int tile = blockIdx.x, cam = blockIdx.y;
     const int tx0 = (tile % tiles_x) * RT_TW, ty0 = (tile / tiles_x) * RT_TH;
     if (threadIdx.x == 0) { s_mm[0] = INT_MAX; s_mm[1] = INT_MAX; s_mm[2] = INT_MIN; s_mm[3] = INT_MIN; }
+    if (threadIdx.x < RT_TH) { s_row[threadIdx.x][0] = INT_MAX; s_row[threadIdx.x][1] = INT_MIN; }
     __syncthreads();
     int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
     for (int i = threadIdx.x; i < RT_TW * RT_TH; i += blockDim.x) {
@@ -228,12 +230,18 @@ __global__ void __launch_bounds__(256) k_rect_tile_bbox(const int2 *__restrict__
             const int2 e = map[((size_t)cam * H + y) * W + x];
             const int xi = e.x >> 5, yi = e.y >> 5;
             x0 = min(x0, xi); x1 = max(x1, xi + 1); y0 = min(y0, yi); y1 = max(y1, yi + 1);
+            atomicMin(&s_row[i / RT_TW][0], yi); atomicMax(&s_row[i / RT_TW][1], yi);
         }
     }
     atomicMin(&s_mm[0], x0); atomicMin(&s_mm[1], y0); atomicMax(&s_mm[2], x1); atomicMax(&s_mm[3], y1);
     __syncthreads();
     // the box origin is rounded down to a 16-byte boundary: TMA needs 16-byte aligned global row starts
-    if (threadIdx.x == 0) tiles[(size_t)cam * ntiles + tile] = make_int4(s_mm[0] & ~15, s_mm[1], s_mm[2], s_mm[3]);
+    if (threadIdx.x == 0) {
+        tiles[(size_t)cam * ntiles + tile] = make_int4(s_mm[0] & ~15, s_mm[1], s_mm[2], s_mm[3]);
+        int span = 0;
+        for (int r = 0; r < RT_TH; r++) if (s_row[r][1] >= s_row[r][0]) span = max(span, s_row[r][1] - s_row[r][0]);
+        atomicMax(&tiles[2 * (size_t)ntiles].x, span);              // plan-wide: steepest destination row (extra entry behind the boxes)
+    }
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -277,10 +285,12 @@ __device__ __forceinline__ uint32_t remap_group_smem(const uint32_t *w, int bww,
     return __byte_perm(p01, p23, 0x5410);
 }
 
-__global__ void __launch_bounds__(RT_THREADS) k_rect_remap_tma(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+template <int RT_STAGES>
+__global__ void __launch_bounds__(RT_THREADS, 3) k_rect_remap_tma(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
                                                                uint8_t *__restrict__ dL, uint8_t *__restrict__ dR, int dp, size_t df,
                                                                const int2 *__restrict__ map, const int4 *__restrict__ tiles,
-                                                               int W, int H, int n, int BW, int BH, int stage_bytes, int tiles_x, int ntiles, int fpb)
+                                                               int W, int H, int n, int BW, int BH, int stage_bytes, int tiles_x, int ntiles, int fpb,
+                                                               int rt_per_lane_base)
 {
     extern __shared__ __align__(128) uint8_t rt_smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(rt_smem + (size_t)RT_STAGES * stage_bytes);
@@ -337,19 +347,78 @@ __global__ void __launch_bounds__(RT_THREADS) k_rect_remap_tma(const __grid_cons
         bool words = live && (ymax - ymin <= 1);
 #pragma unroll
         for (int k = 1; k < 4; k++) words = words && (xi[k] >= xi[0]) && (xi[k] - xi[0] <= 6);
-        const bool three = words && (ymax != ymin);
+        // Row base.  A warp covers 128 destination pixels of one row; under a rectifying rotation their source rows step
+        // once or twice along the way.  If every lane started at its OWN first source row, lanes left and right of a step
+        // would read different box rows in the same LDS -- a bank conflict whenever the box pitch is not a multiple of 128 B
+        // (61 % of the shared wavefronts of the r01 kernel).  With one base row for the whole warp (REDUX min) every LDS
+        // reads consecutive words of ONE row: conflict-free; a pixel whose taps start one row lower just carries a zero
+        // weight for the base row.  Maps too steep for that (more than two source rows under a warp) keep per-lane bases.
+        const int wmin = __reduce_min_sync(0xFFFFFFFFu, words ? ymin : INT_MAX);
+        const int wmax = __reduce_max_sync(0xFFFFFFFFu, words ? ymax : INT_MIN);
+        const bool uni = (wmax - wmin <= 1) && !rt_per_lane_base;
+        const int base = uni ? wmin : ymin;
+        const bool three = words && (uni ? (wmax != wmin) : (ymax != ymin));
         const unsigned any3 = __any_sync(0xFFFFFFFFu, three);
         mode[g] = !live ? 0 : words ? (any3 ? 3 : 2) : 1;
-        o0[g] = ymin * BW + xi[0];
+        o0[g] = base * BW + xi[0];
         mis[g] = (uint32_t)(o0[g] & 3) * 8u;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t dk = (uint32_t)(xi[k] - xi[0]) & 7u;
             selw[g][k] = dk | ((dk + 1) << 4);
-            row_weights(wr[g][k], xf[k], yf[k], yi[k] == ymin);
+            row_weights(wr[g][k], xf[k], yf[k], yi[k] == base);
         }
     }
     uint8_t *dbase = (cam ? dR : dL) + (size_t)f0 * df;
+    static_assert(RT_G == 2, "the fast loop below is written for two rows per thread");
+    if (__all_sync(0xFFFFFFFFu, mode[0] >= 2 && mode[1] >= 2)) {
+        // whole warp on the word path (every full tile of a sane map): branch-free frame loop.  The row count is warp-uniform;
+        // a third row with zero weights is harmless (the stage keeps a spare row behind the box).
+        const bool r3 = (mode[0] == 3) || (mode[1] == 3);
+        uint8_t *d0 = dbase + doff[0], *d1 = dbase + doff[1];
+        const uint32_t w0 = smem_u32(rt_smem) + (uint32_t)(o0[0] & ~3), w1 = smem_u32(rt_smem) + (uint32_t)(o0[1] & ~3);
+        const uint32_t rowb = (uint32_t)BW;
+        auto lds = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+        auto group = [&](uint32_t a, uint32_t mi, const uint32_t (&sel)[4], const uint32_t (&wg)[4][3], bool three_rows) {
+            uint32_t acc[4] = {1u << 15, 1u << 15, 1u << 15, 1u << 15};
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                if (r == 2 && !three_rows) break;
+                const uint32_t a0 = lds(a + r * rowb), a1 = lds(a + r * rowb + 4), a2 = lds(a + r * rowb + 8);
+                const uint32_t lo = __funnelshift_r(a0, a1, mi), hi = __funnelshift_r(a1, a2, mi);
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc[k] = __dp2a_lo(wg[k][r], __byte_perm(lo, hi, sel[k]), acc[k]);
+            }
+            const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
+            return __byte_perm(p01, p23, 0x5410);
+        };
+        // kept out of the compiler's sight: it otherwise re-derives the leader test and both row pointers from %tid every frame
+        uint32_t leader = (lane == 0) ? 1u : 0u;
+        asm volatile("" : "+r"(leader));
+        asm volatile("" : "+l"(d0));
+        asm volatile("" : "+l"(d1));
+        // one trip = one turn of the ring: the stage index, its barriers and its shared-memory offset are compile-time constants
+        uint32_t ph = 0;
+        for (int f = 0; f < nf; f += RT_STAGES) {
+#pragma unroll
+            for (int s = 0; s < RT_STAGES; s++) {
+                if (f + s < nf) {
+                    mbar_wait(&full[s], ph);
+                    const uint32_t soff = (uint32_t)s * (uint32_t)stage_bytes;
+                    uint32_t out0, out1;
+                    if (r3) { out0 = group(w0 + soff, mis[0], selw[0], wr[0], true);  out1 = group(w1 + soff, mis[1], selw[1], wr[1], true); }
+                    else    { out0 = group(w0 + soff, mis[0], selw[0], wr[0], false); out1 = group(w1 + soff, mis[1], selw[1], wr[1], false); }
+                    __syncwarp();
+                    if (leader) mbar_arrive(&empty[s]);
+                    asm volatile("st.global.u32 [%0], %1;" ::"l"(d0), "r"(out0) : "memory");      // (the laundered pointers are generic to the compiler)
+                    asm volatile("st.global.u32 [%0], %1;" ::"l"(d1), "r"(out1) : "memory");
+                    d0 += df; d1 += df;
+                }
+            }
+            ph ^= 1u;
+        }
+        return;
+    }
     for (int f = 0; f < nf; f++) {
         const int s = f % RT_STAGES, kk = f / RT_STAGES;
         mbar_wait(&full[s], (uint32_t)kk & 1u);
@@ -409,15 +478,27 @@ int rect_plan_build(RectPlan &pl, const int2 *map, int W, int H, cudaStream_t s)
     pl.tma = false;
     pl.tiles_x = (W + RT_TW - 1) / RT_TW; pl.tiles_y = (H + RT_TH - 1) / RT_TH;
     const int nt = pl.tiles_x * pl.tiles_y;
-    if (cudaMalloc(&pl.d_tiles, sizeof(int4) * 2 * nt) != cudaSuccess) { pl.d_tiles = nullptr; return 0; }
+    if (cudaMalloc(&pl.d_tiles, sizeof(int4) * (2 * nt + 1)) != cudaSuccess) { pl.d_tiles = nullptr; return 0; }
+    cudaMemsetAsync(pl.d_tiles + 2 * nt, 0, sizeof(int4), s);
     k_rect_tile_bbox<<<dim3(nt, 2), 256, 0, s>>>(map, pl.d_tiles, W, H, pl.tiles_x, nt);
-    int4 *ht = new int4[2 * nt];
-    if (cudaMemcpyAsync(ht, pl.d_tiles, sizeof(int4) * 2 * nt, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+    int4 *ht = new int4[2 * nt + 1];
+    if (cudaMemcpyAsync(ht, pl.d_tiles, sizeof(int4) * (2 * nt + 1), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) { delete[] ht; return 1; }
+    const int row_span = ht[2 * nt].x;
     int bw = 0, bh = 0;
     for (int i = 0; i < 2 * nt; i++) { bw = std::max(bw, ht[i].z - ht[i].x + 1); bh = std::max(bh, ht[i].w - ht[i].y + 1); }
     delete[] ht;
-    pl.BW = align_up(bw, 16); pl.BH = bh;
+    // Box pitch in shared memory = box width.  A destination row (one warp) whose source rows stay within two box rows reads
+    // them through one warp-uniform base row -- conflict-free at any pitch.  Steeper maps (keystone: the shipped set spans up to
+    // 7 source rows under 128 pixels at the top and bottom edge) make the lanes of one LDS read different box rows; those only
+    // stay on distinct banks when the pitch is a multiple of 128 B, so the box is widened to that (more L2->SM bytes, same HBM).
+    const bool steep = row_span > 1;
+    pl.BH = bh;
+    pl.BW = align_up(bw, 16);
+    if ((steep || getenv("U96_RECT_BW128")) && !getenv("U96_RECT_BW16")) {
+        const int wide = align_up(bw, 128);
+        if (wide <= 256 && align_up(wide * (bh + 1) + 16, 128) <= 16384) pl.BW = wide;
+    }
     pl.stage_bytes = align_up(pl.BW * (pl.BH + 1) + 16, 128);     // one spare row + tail for the word path's over-read
     pl.tma = (pl.BW <= 256 && pl.BH <= 255 && pl.stage_bytes <= 16384 && tmap_encoder() != nullptr && !getenv("U96_RECT_LEGACY"));
     return 1;
@@ -445,12 +526,37 @@ int launch_rect_remap(const uint8_t *srcL, const uint8_t *srcR, int src_pitch, s
             encode_src_map(&tmR, srcR, src_pitch, src_frame, W, H, n, pl.BW, pl.BH)) {
             const int nt = pl.tiles_x * pl.tiles_y;
             static const int fpb_env = getenv("U96_RECT_FPB") ? atoi(getenv("U96_RECT_FPB")) : 0;
-            const int fpb = fpb_env > 0 ? fpb_env : 32;
-            const int smem = RT_STAGES * pl.stage_bytes + 2 * RT_STAGES * (int)sizeof(uint64_t);
-            cudaFuncSetAttribute(k_rect_remap_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_STAGES * 16384 + 128);
+            int fpb = fpb_env;
+            if (fpb <= 0) {
+                // every CTA pays a set-up worth ~6 frames (map entries -> weights); the grid drains through `slots` resident CTAs and
+                // ends with about one CTA duration of partially filled machine: time ~ work / slots + one CTA  (fitted on C2 and C4:
+                // a ceil()-per-wave model picks far too few, too long CTAs)
+                int dev = 0, sms = 148;
+                cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const double slots = 3.0 * sms, per = 2.0 * nt;
+                double best = -1.0;
+                for (int nz = 1; nz <= 64 && nz <= n; nz++) {
+                    const int len = (n + nz - 1) / nz;
+                    if (len < 8 && nz > 1) break;
+                    const double cost = per * (n + 6.0 * ((n + len - 1) / len)) / slots + (len + 6.0);
+                    if (best < 0 || cost < best) { best = cost; fpb = len; }
+                }
+            }
+            static const int per_lane = getenv("U96_RECT_PER_LANE_BASE") ? 1 : 0;      // developer switch: the r01 behaviour
+            static const int st_env = getenv("U96_RECT_STAGES") ? atoi(getenv("U96_RECT_STAGES")) : 0;
+            // small boxes (gentle maps) want a deeper ring to cover the TMA latency; the wide boxes of steep maps carry enough bytes per stage
+            const int stages = st_env > 0 ? st_env : (pl.stage_bytes <= 4096 ? 8 : 4);
             dim3 grid(nt, 2, (n + fpb - 1) / fpb);
-            k_rect_remap_tma<<<grid, RT_THREADS, smem, s>>>(tmL, tmR, dstL.p, dstR.p, dstL.pitch, dstL.frame, map, pl.d_tiles, W, H, n,
-                                                            pl.BW, pl.BH, pl.stage_bytes, pl.tiles_x, nt, fpb);
+            auto go = [&](auto kern, int st) {
+                const int smem = st * pl.stage_bytes + 2 * st * (int)sizeof(uint64_t);
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, st * 16384 + 256);
+                kern<<<grid, RT_THREADS, smem, s>>>(tmL, tmR, dstL.p, dstR.p, dstL.pitch, dstL.frame, map, pl.d_tiles, W, H, n,
+                                                    pl.BW, pl.BH, pl.stage_bytes, pl.tiles_x, nt, fpb, per_lane);
+            };
+            if (stages >= 12) go(k_rect_remap_tma<12>, 12);
+            else if (stages >= 8) go(k_rect_remap_tma<8>, 8);
+            else if (stages >= 6) go(k_rect_remap_tma<6>, 6);
+            else go(k_rect_remap_tma<4>, 4);
             return 1;
         }
     }
