@@ -65,38 +65,93 @@ __device__ __forceinline__ void uf_union(int *label, int a, int b)
     }
 }
 
-__global__ void __launch_bounds__(256) k_cc_init(const int16_t *__restrict__ disp, int dpitch, size_t dframe, int W, int H, int *label, int *size)
+// connected(p, q) of filterSpeckles: both valid and their 16x disparities differ by at most maxDiff
+__device__ __forceinline__ bool cc_conn(int a, int b, int maxdiff) { return a != INVALID16 && b != INVALID16 && abs(a - b) <= maxdiff; }
+
+// Pass 1, one CTA per image row: horizontal runs.  label[i] = pixel index of the first pixel of the run i belongs to (-1 for an
+// invalid pixel).  Every thread owns K consecutive pixels; "the last cut (run start, or an invalid pixel = no open run) at or before
+// x" is a prefix scan with the operator combine(a, b) = b has a cut ? b : a -- no atomics, one write per pixel.  size[] is cleared at
+// run starts only (the only indices that can ever become roots).
+__global__ void __launch_bounds__(256) k_cc_rows(const int16_t *__restrict__ disp, int dpitch, size_t dframe, int W, int H, int maxdiff,
+                                                 int *__restrict__ label, int *__restrict__ size)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
-    if (i >= W * H) return;
-    const int y = i / W, x = i - y * W;
-    const int d = disp[(size_t)f * dframe + (size_t)y * dpitch + x];
-    label[(size_t)f * W * H + i] = (d == INVALID16) ? -1 : i;
-    size[(size_t)f * W * H + i] = 0;
+    __shared__ int s_cut[8], s_val[8];
+    const int y = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int16_t *row = disp + (size_t)f * dframe + (size_t)y * dpitch;
+    int *lab = label + ((size_t)f * H + y) * W, *sz = size + ((size_t)f * H + y) * W;
+    const int K = (W + 255) / 256;
+    const int x0 = tid * K;
+    const int before = (x0 > 0 && x0 - 1 < W) ? row[x0 - 1] : INVALID16;
+    int hc = 0, v = -1, prev = before;
+    for (int k = 0; k < K && x0 + k < W; k++) {
+        const int d = row[x0 + k];
+        if (d == INVALID16) { hc = 1; v = -1; }
+        else if (!cc_conn(prev, d, maxdiff)) { hc = 1; v = x0 + k; }
+        prev = d;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                          // inclusive scan inside the warp
+        const int phc = __shfl_up_sync(0xFFFFFFFFu, hc, o), pv = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o && !hc) { hc = phc; v = pv; }
+    }
+    if (lane == 31) { s_cut[warp] = hc; s_val[warp] = v; }
+    __syncthreads();
+    int ehc = __shfl_up_sync(0xFFFFFFFFu, hc, 1), cur = __shfl_up_sync(0xFFFFFFFFu, v, 1);      // exclusive: threads before this one
+    if (lane == 0) ehc = 0;
+    if (!ehc) {
+        cur = -1;
+        for (int w = warp - 1; w >= 0; w--)
+            if (s_cut[w]) { cur = s_val[w]; break; }
+    }
+    prev = before;
+    for (int k = 0; k < K && x0 + k < W; k++) {
+        const int x = x0 + k, d = row[x];
+        if (d == INVALID16) cur = -1;
+        else if (!cc_conn(prev, d, maxdiff)) { cur = x; sz[x] = 0; }
+        lab[x] = (d == INVALID16) ? -1 : y * W + cur;
+        prev = d;
+    }
 }
 
-__global__ void __launch_bounds__(256) k_cc_merge(const int16_t *__restrict__ disp, int dpitch, size_t dframe, int W, int H, int maxdiff, int *label)
+// Pass 2: vertical links.  Two runs of adjacent rows are united once, by the first pixel of their overlap that is vertically
+// connected (a pixel whose left neighbour already linked the same two runs skips) -- unions per run pair, not per pixel.
+__global__ void __launch_bounds__(256) k_cc_vmerge(const int16_t *__restrict__ disp, int dpitch, size_t dframe, int W, int H, int maxdiff, int *label)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (i >= W * H || i < W) return;
+    const int y = i / W, x = i - y * W;
+    const int16_t *r1 = disp + (size_t)f * dframe + (size_t)y * dpitch, *r0 = r1 - dpitch;
+    const int d = r1[x], u = r0[x];
+    if (!cc_conn(d, u, maxdiff)) return;
+    if (x > 0) {
+        const int dl = r1[x - 1], ul = r0[x - 1];
+        if (cc_conn(dl, d, maxdiff) && cc_conn(ul, u, maxdiff) && cc_conn(dl, ul, maxdiff)) return;     // the same two runs, already linked
+    }
+    int *lab = label + (size_t)f * W * H;
+    uf_union(lab, lab[i], lab[i - W]);
+}
+
+// Pass 3: component sizes, one atomicAdd per run (by its last pixel); run starts are compressed to their root on the way.
+__global__ void __launch_bounds__(256) k_cc_count(const int16_t *__restrict__ disp, int dpitch, size_t dframe, int W, int H, int maxdiff,
+                                                  int max_size, int *label, int *size)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
     if (i >= W * H) return;
     const int y = i / W, x = i - y * W;
-    const int16_t *img = disp + (size_t)f * dframe;
-    int *lab = label + (size_t)f * W * H;
-    const int d = img[(size_t)y * dpitch + x];
+    const int16_t *row = disp + (size_t)f * dframe + (size_t)y * dpitch;
+    const int d = row[x];
     if (d == INVALID16) return;
-    if (x + 1 < W) { const int e = img[(size_t)y * dpitch + x + 1]; if (e != INVALID16 && abs(e - d) <= maxdiff) uf_union(lab, i, i + 1); }
-    if (y + 1 < H) { const int e = img[(size_t)(y + 1) * dpitch + x]; if (e != INVALID16 && abs(e - d) <= maxdiff) uf_union(lab, i, i + W); }
-}
-
-__global__ void __launch_bounds__(256) k_cc_count(int W, int H, int *label, int *size)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
-    if (i >= W * H) return;
+    if (x + 1 < W && cc_conn(d, row[x + 1], maxdiff)) return;   // not the last pixel of its run
     int *lab = label + (size_t)f * W * H;
-    if (lab[i] < 0) return;
-    const int r = uf_find(lab, i);
-    lab[i] = r;                                             // path compression (roots never change any more)
-    atomicAdd(&size[(size_t)f * W * H + r], 1);
+    // first pixel of the run: every pixel but the first still holds it (only run starts are ever hooked under another root)
+    const bool is_start = (x == 0) || !cc_conn(row[x - 1], d, maxdiff);
+    const int s = is_start ? i : lab[i];
+    const int r = uf_find(lab, s);
+    if (r != s) lab[s] = r;                                     // path compression for pass 4 (roots never change any more)
+    // only "at most max_size or more" matters: a component already known to be large takes no further atomics (the counter is
+    // monotonic, a stale read merely adds once more) -- the big background components would otherwise serialise thousands of runs
+    int *cnt = &size[(size_t)f * W * H + r];
+    if (*reinterpret_cast<volatile int *>(cnt) <= max_size) atomicAdd(cnt, i - s + 1);
 }
 
 __global__ void __launch_bounds__(256) k_cc_apply(int16_t *__restrict__ disp, int dpitch, size_t dframe, int W, int H, int max_size,
@@ -125,9 +180,9 @@ int launch_postfilter(Img16 disp, const int16_t *cost, int W, int H, int n, int 
     if (speckle_window > 0 && speckle_range >= 0 && scratch) {
         int *label = scratch, *size = scratch + (size_t)n * W * H;
         const dim3 grid((W * H + 255) / 256, n);
-        k_cc_init<<<grid, 256, 0, s>>>(disp.p, disp.pitch, disp.frame, W, H, label, size);
-        k_cc_merge<<<grid, 256, 0, s>>>(disp.p, disp.pitch, disp.frame, W, H, speckle_range, label);
-        k_cc_count<<<grid, 256, 0, s>>>(W, H, label, size);
+        k_cc_rows<<<dim3(H, n), 256, 0, s>>>(disp.p, disp.pitch, disp.frame, W, H, speckle_range, label, size);
+        k_cc_vmerge<<<grid, 256, 0, s>>>(disp.p, disp.pitch, disp.frame, W, H, speckle_range, label);
+        k_cc_count<<<grid, 256, 0, s>>>(disp.p, disp.pitch, disp.frame, W, H, speckle_range, speckle_window, label, size);
         k_cc_apply<<<grid, 256, 0, s>>>(disp.p, disp.pitch, disp.frame, W, H, speckle_window, label, size);
         launches += 4;
     }
