@@ -662,6 +662,38 @@ def test_bm_rtl_uniqueness_across_slices(u, fe640, golden, oracle, D, B, thr):
     assert np.array_equal(d, want), int((d != want).sum())
 
 
+def test_cluster_ring_under_scheduling_noise(u, oracle):
+    """the DSMEM record ring of the cluster kernels (D = 128 / 256) releases its slots with a relaxed remote arrive.
+    Stress it: many launches of both cluster sizes and both profiles while a second handle keeps unrelated kernels running on
+    other streams (CTAs of a cluster then drift apart as their SMs are shared unevenly); every frame of every launch must equal
+    the oracle / the first launch bit for bit."""
+    W, H = 600, 200
+    noise = u.StereoFrontEnd(0, 640, 480, 24)
+    noise.set_bm_params(width=640, height=480, profile=0, block_size=9, num_disparities=64, x_store_offset=1)
+    nL, nR = u.synth_batch(9, 0, 24, 640, 480, 64)
+    try:
+        for D, prof in ((128, 0), (256, 0), (128, 1), (256, 1)):
+            L, R = u.synth_batch(4, D, 6, W, H, D)
+            with u.StereoFrontEnd(0, W, H, 6) as fe:
+                if prof == 0:
+                    fe.set_bm_params(width=W, height=H, profile=0, block_size=21, num_disparities=D, uni_enable=1, uni_thr=900, x_store_offset=1, rtl_extended=1)
+                    want = [oracle.bm_rtl(oracle.xsobel_rtl(L[i]), oracle.xsobel_rtl(R[i]), wsz=21, ndisp=D, uni_enb=1, uni_thr=900, rtl_extended=1,
+                                          bitserial_div=0) for i in range(6)]
+                else:
+                    fe.set_bm_params(width=W, height=H, profile=1, block_size=15, num_disparities=D, prefilter_cap=31, texture_threshold=10, uniqueness_ratio=10)
+                    want = [oracle.bm_cv(oracle.xsobel_cv(L[i]), oracle.xsobel_cv(R[i]), wsz=15, ndisp=D) for i in range(6)]
+                for it in range(40):
+                    noise.submit_rect(it & 1, nL, nR)                 # in flight on its own stream while the cluster kernel runs
+                    fe.submit_rect(it & 1, L, R)
+                    b = fe.wait()
+                    d = fe.receive_disp(b)
+                    noise.wait()
+                    for i in range(6):
+                        assert np.array_equal(d[i], want[i]), (D, prof, it, i)
+    finally:
+        noise.close()
+
+
 def test_fast_and_generic_bm_kernels_agree(u, monkeypatch):
     """The generic kernel (U96_BM_GENERIC=1) and the fast path produce identical maps on a ragged width."""
     W, H, D = 1000, 131, 128

@@ -452,8 +452,10 @@ static void bm_launch_t(const BmArgs &a, dim3 grid, int smem, cudaStream_t s)
     k_bm<PROFILE, SAT><<<grid, BM_THREADS, smem, s>>>(a);
 }
 
-int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
-              const BmConfig &c, int n, cudaStream_t s)
+// The border of the disparity map (everything outside the valid rectangle) holds the invalid code.  The BM kernels never write
+// it, so -- like the firmware, which memsets the DISP banks once at start-up (fpga.c:105-106) and lets bm_obuf2.v skip those bursts
+// -- the C ABI fills it once per bank and configuration instead of once per submit.
+int launch_bm_border(Img16 disp, const BmConfig &c, int n, cudaStream_t s)
 {
     const int16_t inv = (c.profile == U96_PROFILE_RTL) ? (int16_t)-1 : (int16_t)-16;
     {
@@ -464,12 +466,18 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
         const int y_lo = ok ? b.y_lo : c.H, y_hi = ok ? b.y_hi : c.H, x_lo = ok ? b.ctr_lo + off : c.W, x_hi = ok ? b.ctr_hi + off : c.W;
         k_fill_border<<<dim3((c.H + FB_ROWS - 1) / FB_ROWS, n), 256, 0, s>>>(disp.p, disp.pitch, disp.frame, c.W, c.H, y_lo, y_hi, x_lo, x_hi, inv);
     }
+    return 1;
+}
+
+int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
+              const BmConfig &c, int n, cudaStream_t s)
+{
     if (bm_fast_supported(c) && !getenv("U96_BM_GENERIC")) {
         const int k = launch_bm_fast(xl, xr, pitch, frame, disp, c, n, s);
-        if (k) return 1 + k;
+        if (k) return k;
     }
     BmArgs a;
-    if (!bm_fill_args(c, a)) return 1;
+    if (!bm_fill_args(c, a)) return 0;
     a.xl = xl; a.xr = xr; a.disp = disp.p; a.cost = c.cost; a.pitch = pitch; a.frame = frame;
     a.dpitch = disp.pitch; a.dframe = disp.frame;
     const int smem = bm_smem_bytes(c);
@@ -479,7 +487,7 @@ int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img
         if (sat) bm_launch_t<U96_PROFILE_RTL, true>(a, grid, smem, s);
         else bm_launch_t<U96_PROFILE_RTL, false>(a, grid, smem, s);
     } else bm_launch_t<U96_PROFILE_OPENCV, false>(a, grid, smem, s);
-    return 2;
+    return 1;
 }
 
 }  // namespace u96

@@ -44,6 +44,8 @@ int  bm_smem_bytes(const BmConfig &c);
 int  bm_wave_frames(const BmConfig &c);
 int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
               const BmConfig &c, int n, cudaStream_t s);
+// invalid code into everything outside the valid rectangle of n frames (the BM kernels never write there)
+int launch_bm_border(Img16 disp, const BmConfig &c, int n, cudaStream_t s);
 
 bool bm_fast_supported(const BmConfig &c);
 int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,

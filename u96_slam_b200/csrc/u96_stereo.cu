@@ -74,6 +74,7 @@ struct Bank {
     bool filled = false, pending = false;
     bool has_disp = false;              // the kernels ran (false after u96_set_rect_image until u96_start_xsbl)
     bool staged = false;                // pipelined submit: per-stage events were not recorded
+    uint64_t border_sig = 0;            // configuration the border of the DISP bank was filled for (0 = never)
     cudaStream_t stream = nullptr;
     cudaStream_t sub[3] = {nullptr, nullptr, nullptr};      // chunk pipeline: H2D / kernels / D2H of different chunks overlap
     cudaEvent_t sub_ev[3] = {nullptr, nullptr, nullptr};
@@ -376,6 +377,21 @@ static int ensure_bank_buffers(u96_handle *h, Bank &k, int from, int n, bool hos
     return U96_OK;
 }
 
+// The DISP bank's border (outside the valid rectangle) is written once per bank and configuration: the BM kernels never touch it
+// (the firmware memsets the DDR banks once, fpga.c:105-106).  All maxB frames are filled, so later submits of any batch size hold.
+static int ensure_border(u96_handle *h, Bank &k, cudaStream_t s)
+{
+    const u96_bm_params &p = h->bm;
+    const uint64_t sig = 1ull | ((uint64_t)p.profile << 1) | ((uint64_t)p.width << 4) | ((uint64_t)p.height << 20) |
+                         ((uint64_t)p.num_disparities << 36) | ((uint64_t)p.block_size << 48) | ((uint64_t)(p.x_store_offset & 1) << 56);
+    if (k.border_sig == sig) return U96_OK;
+    const Img16 disp{k.disp, h->pitch, (size_t)h->pitch * p.height};
+    h->launches += launch_bm_border(disp, bm_config(p), h->maxB, s);
+    CK(cudaGetLastError());
+    k.border_sig = sig;
+    return U96_OK;
+}
+
 // kernels of frames [f0, f0+nf) of a bank on stream s; `prof` records the Perf-style stage events
 static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStream_t s, bool prof)
 {
@@ -475,6 +491,7 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     k.n = n; k.from = from;
 
     // ---- from here on work is enqueued: errors drain the bank before they are returned (abort_submit) ----
+    if (!upload_only) { const int rc = ensure_border(h, k, s); if (rc != U96_OK) return abort_submit(h, k, s, rc); }
     const bool prof = h->profiling && !upload_only;
     if (prof) CKA(cudaEventRecord(k.ev[0], s));
     const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= 64 && !upload_only;
@@ -590,6 +607,7 @@ int u96_start_xsbl(u96_handle *h, int bank)
     { const int rc = ensure_bank_buffers(h, k, FROM_RECT, k.n, false); if (rc != U96_OK) return rc; }
     k.has_eig = h->gftt;
     k.staged = false;
+    { const int rc = ensure_border(h, k, s); if (rc != U96_OK) return abort_submit(h, k, s, rc); }
     const bool prof = h->profiling;
     if (prof) { CKA(cudaEventRecord(k.ev[0], s)); CKA(cudaEventRecord(k.ev[1], s)); }
     const int rc = run_range(h, k, FROM_RECT, 0, k.n, s, prof);
