@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libu96stereo.so")
-SOURCES = ["u96_stereo.cu", "rect.cu", "xsobel.cu", "bm.cu", "bm_fast_cs1.cu", "bm_fast_cs2.cu", "bm_fast_cs4.cu", "reproject.cu", "uvc.cu", "gftt.cu", "postfilter.cu", "microbench.cu"]
+SOURCES = ["u96_stereo.cu", "rect.cu", "xsobel.cu", "bm.cu", "bm_fast_cs1.cu", "bm_fast_cs2.cu", "bm_fast_cs4.cu", "bm_fused.cu", "reproject.cu", "uvc.cu", "gftt.cu", "postfilter.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 OBJDIR = os.path.join(PKG, "lib", "obj")
