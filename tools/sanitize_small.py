@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import u96_slam_b200 as u  # noqa: E402
 
-CONFIGS = ((640, 96, 64, 21, 0, 0), (640, 96, 64, 21, 0, 1), (640, 96, 64, 15, 1, 0), (330, 80, 128, 9, 0, 0),
+CONFIGS = ((640, 96, 64, 21, 0, 0), (640, 96, 64, 15, 0, 0), (640, 96, 64, 21, 0, 1), (640, 96, 64, 15, 1, 0), (330, 80, 128, 9, 0, 0),
                                 (330, 80, 128, 9, 1, 0), (530, 70, 256, 21, 0, 0), (530, 70, 256, 11, 1, 0), (200, 64, 96, 7, 0, 0))
 rot = int(sys.argv[1]) if len(sys.argv) > 1 else 0                     # start with another configuration (first-launch effects)
 cnt = int(sys.argv[2]) if len(sys.argv) > 2 else len(CONFIGS)           # only the first cnt configurations (initcheck is slow)
@@ -30,4 +30,8 @@ for (W, H, D, B, prof, uni) in (CONFIGS[rot:] + CONFIGS[:rot])[:cnt]:
         fe.wait()
         d = fe.receive_disp(0)
         fe.receive_rect(0); fe.receive_xsbl(0); fe.receive_eigen(0)
+        P_l = np.array([[370.0, 0, 313.0, 0], [0, 917.0, 236.0, 0], [0, 0, 1, 0]]); P_r = P_l.copy(); P_r[0, 3] = -199.0
+        fe.reproject_ex(0, P_l, P_r, 4, u.LOCAL_TRANSFORM, np.tile(np.eye(3, 4, dtype=np.float32).reshape(1, 12), (n, 1)))
+        fe.reproject_points(0, P_l, P_r, np.array([[1.5, 2.5], [W - 1.0, H - 1.0], [-3.0, 0.0]], np.float32), 1)
+        fe.receive_uvc(0, u.UVC_BM)
         print(W, H, D, B, prof, uni, "checksum", int(d.astype(np.int64).sum()), flush=True)

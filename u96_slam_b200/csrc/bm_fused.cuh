@@ -35,7 +35,9 @@ constexpr int U_NT = 32 * U_CW + 64;                   // compute | staging warp
 constexpr int U_PREB = U96_FUSED_PREB;                 // prefix buffers: 2 = one barrier per row, 3 CTAs per SM; 1 = a second (compute-only) barrier, 4 CTAs per SM
 
 struct FusedSmem {
-    uint4 pre[U_PREB][U_NC][8];            // 20480 B per buffer  inclusive prefix sums inside a segment: [buffer][column][group] = 8 x u16
+    uint4 pre[U_PREB][U_NC + 8][8];        // 21504 B per buffer  inclusive prefix sums inside a segment: [buffer][column][group] = 8 x u16;
+                                           //          8 never-written pad columns: the unrolled sweep of the last segment reads up to 7 columns past the
+                                           //          tile for pixels nobody finishes -- stable memory instead of a neighbour array (racecheck)
     uint16_t sad[U_NC][U_SADP];            // 23040 B  window sums of the row in flight (rows private to the owning warp)
     uint32_t pmin[U_NSEG][72];             //  5760 B  packed minima [segment][pixel j][group] (odd | even disparities); 72-word segment stride: the
                                            //          four segments of a warp store to disjoint banks
