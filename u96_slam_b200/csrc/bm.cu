@@ -417,12 +417,11 @@ bool bm_fast_supported(const BmConfig &c)
 int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
                    const BmConfig &c, int n, cudaStream_t s)
 {
-    // RTL profile, 64 disparities, uniqueness off: the fused-role kernel (bm_fused.cuh) wins where the column sums are exact (window
-    // <= 16: 2.22 vs 2.59 ms per 296 frames at window 15); with the 10-bit saturating update (window >= 17, e.g. the shipped 21) it
-    // is ALU-bound and k_bm_fast stays ahead (2.53 vs 2.45 ms).  U96_BM_FUSED = 0 / 1 forces one or the other (developer switch).
+    // RTL profile, uniqueness off: the fused-role kernel (bm_fused.cuh).  U96_BM_FUSED = 0 / 1 forces k_bm_fast / k_bm_fused
+    // wherever both apply (developer switch); the default follows the measurements in profiles/r02_summary.md.
     static const int fused_env = getenv("U96_BM_FUSED") ? atoi(getenv("U96_BM_FUSED")) : -1;
     const bool sat = (c.profile == U96_PROFILE_RTL) && (c.wsz * 63 > 1023);
-    if (c.D == 64 && bm_fused_ok(c) && (fused_env == 1 || (fused_env != 0 && !sat))) return launch_bm_fused_rtl64(xl, xr, pitch, frame, disp, c, n, s);
+    if (bm_fused_ok(c) && (fused_env == 1 || (fused_env != 0 && bm_fused_preferred(c, sat)))) return launch_bm_fused_rtl(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 64) return launch_bm_fast_cs1(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 128) return launch_bm_fast_cs2(xl, xr, pitch, frame, disp, c, n, s);
     return launch_bm_fast_cs4(xl, xr, pitch, frame, disp, c, n, s);

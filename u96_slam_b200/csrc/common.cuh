@@ -52,9 +52,10 @@ int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame
                    const BmConfig &c, int n, cudaStream_t s);
 int launch_bm_fast_cs1(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
 int launch_bm_fast_cs2(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
-// fused-role kernel (bm_fused.cuh): RTL profile, 64 disparities, uniqueness off
+// fused-role kernel (bm_fused.cuh): RTL profile, 64 / 128 / 256 disparities, uniqueness off
 bool bm_fused_ok(const BmConfig &c);
-int launch_bm_fused_rtl64(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
+bool bm_fused_preferred(const BmConfig &c, bool sat);
+int launch_bm_fused_rtl(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
 int launch_bm_fast_cs4(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp, const BmConfig &c, int n, cudaStream_t s);
 
 // cv::StereoBM post filters (OPENCV profile): validateDisparity then filterSpeckles; scratch = 2 int32 per pixel of the batch
