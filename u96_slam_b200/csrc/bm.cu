@@ -414,21 +414,28 @@ bool bm_fast_supported(const BmConfig &c)
     return c.profile == U96_PROFILE_RTL;
 }
 
+// does launch_bm_fast hand this configuration to the fused-role kernel?
+static bool bm_takes_fused(const BmConfig &c)
+{
+    static const int fused_env = getenv("U96_BM_FUSED") ? atoi(getenv("U96_BM_FUSED")) : -1;
+    const bool sat = (c.profile == U96_PROFILE_RTL) && (c.wsz * 63 > 1023);
+    return bm_fused_ok(c) && (fused_env == 1 || (fused_env != 0 && bm_fused_preferred(c, sat)));
+}
+
 int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
                    const BmConfig &c, int n, cudaStream_t s)
 {
-    // RTL profile, uniqueness off: the fused-role kernel (bm_fused.cuh).  U96_BM_FUSED = 0 / 1 forces k_bm_fast / k_bm_fused
-    // wherever both apply (developer switch); the default follows the measurements in profiles/r02_summary.md.
-    static const int fused_env = getenv("U96_BM_FUSED") ? atoi(getenv("U96_BM_FUSED")) : -1;
-    const bool sat = (c.profile == U96_PROFILE_RTL) && (c.wsz * 63 > 1023);
-    if (bm_fused_ok(c) && (fused_env == 1 || (fused_env != 0 && bm_fused_preferred(c, sat)))) return launch_bm_fused_rtl(xl, xr, pitch, frame, disp, c, n, s);
+    // the fused-role kernel (bm_fused.cuh) wherever it is the faster one (profiles/r02_summary.md); U96_BM_FUSED = 0 / 1 forces
+    // k_bm_fast / k_bm_fused where both apply (developer switch)
+    if (bm_takes_fused(c)) return launch_bm_fused_rtl(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 64) return launch_bm_fast_cs1(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 128) return launch_bm_fast_cs2(xl, xr, pitch, frame, disp, c, n, s);
     return launch_bm_fast_cs4(xl, xr, pitch, frame, disp, c, n, s);
 }
 
-// Frames whose BM grid fills the device exactly once (2 CTAs per SM on the fast path): the chunk pipeline of the
-// C ABI cuts host batches at multiples of this so that no chunk runs the SMs half empty.
+// Frames whose BM grid fills the device exactly once: the chunk pipeline of the C ABI cuts host batches at multiples of this so
+// that no chunk runs the SMs half empty.  k_bm_fast: 2 CTAs per SM, one CTA per tile and 64-disparity slice; k_bm_fused: 4 / 2 / 1
+// CTAs per SM at 64 / 128 / 256 disparities, one CTA per tile.
 int bm_wave_frames(const BmConfig &c)
 {
     int dev = 0, sms = 148;
@@ -438,6 +445,10 @@ int bm_wave_frames(const BmConfig &c)
     const int ncen = (c.profile == U96_PROFILE_RTL) ? (c.W - 2 - h) - (c.D + h) + 1 : (c.W - 1 - h) - (c.D - 1 + h) + 1;
     if (ncen <= 0) return 1;
     const int tx5 = 160 - 2 * h, tx4 = 128 - 2 * h;
+    if (bm_takes_fused(c)) {
+        const int tiles = (ncen + tx5 - 1) / tx5, occ = (c.D == 64) ? 4 : (c.D == 128) ? 2 : 1;
+        return std::max(1, (occ * sms + tiles - 1) / tiles);
+    }
     const int tiles = std::min((ncen + tx5 - 1) / tx5, (ncen + tx4 - 1) / tx4) * std::max(1, c.D / 64);
     return std::max(1, (2 * sms + tiles - 1) / tiles);
 }

@@ -1,5 +1,6 @@
-// bm_fused.cuh -- SAD block matching with ONE compute role, sm_100a (RTL profile, 64 / 128 / 256 disparities, uniqueness off:
-// the shipped register set, fpga.c:150-160).  Same arithmetic as bm_fast.cuh / bm.cu; different mapping.
+// bm_fused.cuh -- SAD block matching with ONE compute role, sm_100a: 64 / 128 / 256 disparities, RTL profile with the uniqueness
+// filter off (the shipped register set, fpga.c:150-160) and the cv::StereoBM profile (texture, exact uniqueness, mirrored
+// sub-pixel neighbours).  Same arithmetic as bm_fast.cuh / bm.cu; different mapping.
 //
 // Why: ncu shows k_bm_fast bound by the shared-memory pipe (l1tex__data_pipe_lsu_wavefronts_mem_shared 77-80 % of peak, ALU pipe
 // 62 %): its V warps (thread = column) and H warps (lane = segment x disparity group) hold the column sums in two different
@@ -40,8 +41,10 @@ struct FusedSmem {
     uint16_t sad[U_NC][SADP];              // window sums of the row in flight; pitch 2D+16 B: rows skew over the banks
     uint32_t pmin[U_NSEG][PMS];            // packed minima [segment][pixel j][group] (odd | even disparities); 9*NG-word segment stride: the
                                            // segments of a warp store to disjoint banks
-    uint32_t ckey[U_NC][NCH];              // per pixel: one key (min SAD << 8 | group) per 64-disparity chunk
-    uint16_t guard[2][2][U_NC + 8];        // [buffer][d=-1 / d=D][column] column sums of the guard lanes
+    uint32_t ckey[U_NC][2];                // per pixel: winner key (min SAD << 8 | group code) and, OPENCV, the smallest group minimum outside the
+                                           // winner's group and its two neighbours
+    uint32_t gt[2][U_NC + 8];              // output of the guard warp, [buffer]: RTL = u16 [d=-1 / d=D][column] column sums of the guard lanes;
+                                           // OPENCV = u32 [1 + column] prefix sums over the columns of the texture column sums (entry 0 = 0)
     uint8_t rrow[2][2][RLEN];              // [buffer][newest / oldest] R row segment: R[xs - D - 8 .. xs + 168)
     uint32_t lrow4[2][2][U_NC];            // L row segment, every pixel replicated into the four bytes of a word (VABSDIFF4 operand)
     uint8_t lrow[2][2][U_NC];              // L row segment (guard warp: 8 columns per word pair)
@@ -63,9 +66,10 @@ __device__ __forceinline__ uint2 r_window(uint2 a, uint2 b, int i)
 // resident CTAs per SM: 64 disparities 4 (54.5 KB, 72 registers), 128: 2, 256: 1
 __host__ __device__ constexpr int fused_occupancy(int ng) { return ng == 8 ? 4 : ng == 16 ? 2 : 1; }
 
-template <bool SAT, int NG>
+template <int PROFILE, bool SAT, int NG>
 __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fused(const FastArgs a)
 {
+    constexpr bool CV = (PROFILE == U96_PROFILE_OPENCV);
     using SM = FusedSmem<NG>;
     constexpr int D = SM::D, RLEN = SM::RLEN, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
         // finishing pass: lane = pixel, on the first five compute warps
         const int px = 32 * warp + lane;
         const bool px_ok = (warp < 5) && (px < ntx);
-        const int out_x = ctr0 + px + a.x_store_offset;
+        const int out_x = ctr0 + px + (CV ? 0 : a.x_store_offset);
         int16_t *out_p = gout + (ptrdiff_t)(yb0 - (wsz - 1)) * (ptrdiff_t)a.dpitch + out_x;   // row of iteration 0 (not dereferenced before wsz-1)
 
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");        // rows of iteration 0 are staged
@@ -156,44 +160,109 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                     }
                 }
                 __syncwarp();
-                // ---- chunk pass (warp-local): 8 packed minima -> one key per (pixel, 64-disparity chunk); lowest group wins ties ----
-                if (it_px < ntx) {
-                    const uint32_t *pm = &sm.pmin[it_px >> 3][NG * (it_px & 7) + 8 * it_ch];
+                // ---- chunk pass (warp-local, lane = (pixel, 64-disparity chunk)): 8 packed minima -> the chunk's key; the NCH lanes of
+                //      a pixel then agree on the winner by shuffles.  Group code = group (RTL: the lower disparity wins a tie,
+                //      bm_calc_det.v / bm_calc_upd.v strict <) or 255 - group (OPENCV: the higher one, reverse scan) ----
+                {
+                    const bool live = it_px < ntx;
+                    const uint32_t *pm = &sm.pmin[(live ? it_px : 0) >> 3][NG * ((live ? it_px : 0) & 7) + 8 * it_ch];
                     const uint4 pa = *reinterpret_cast<const uint4 *>(pm), pb = *reinterpret_cast<const uint4 *>(pm + 4);
-                    const uint32_t g0 = 8u * it_ch;
-                    auto gk = [](uint32_t m, uint32_t gi) { return (min(m & 0xFFFFu, m >> 16) << 8) | gi; };
-                    uint32_t best = __vimin3_u32(gk(pa.x, g0), gk(pa.y, g0 + 1), gk(pa.z, g0 + 2));
-                    best = __vimin3_u32(best, gk(pa.w, g0 + 3), gk(pb.x, g0 + 4));
-                    best = __vimin3_u32(best, gk(pb.y, g0 + 5), gk(pb.z, g0 + 6));
-                    sm.ckey[it_px][it_ch] = min(best, gk(pb.w, g0 + 7));
-                }
-                asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");  // every prefix entry has been read (the next row may overwrite them); chunk keys and window sums are visible
-                // ---- finishing pass: lane = pixel: winner, neighbours, sub-pixel fraction, output (bm_calc_det / upd / frac / obuf2) ----
-                if (px_ok) {
-                    uint32_t best = sm.ckey[px][0];
+                    const uint32_t m8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+                    uint32_t gm[8], key[8];
 #pragma unroll
-                    for (int k = 1; k < NCH; k++) best = min(best, sm.ckey[px][k]);
-                    const uint32_t mv = best >> 8; const int gs = best & 0xFF;
+                    for (int k = 0; k < 8; k++) {
+                        gm[k] = min(m8[k] & 0xFFFFu, m8[k] >> 16);
+                        const uint32_t gi = 8u * it_ch + k;
+                        key[k] = (gm[k] << 8) | (CV ? 255u - gi : gi);
+                    }
+                    uint32_t best = __vimin3_u32(key[0], key[1], key[2]);
+                    best = __vimin3_u32(best, key[3], key[4]);
+                    best = __vimin3_u32(best, key[5], key[6]);
+                    best = min(best, key[7]);
+#pragma unroll
+                    for (int o = 1; o < NCH; o <<= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+                    uint32_t um = 0xFFFFu;
+                    if (CV) {
+                        // smallest group minimum outside the winner's group and its two neighbours (those three are rescanned exactly below)
+                        const int gs = 255 - (int)(best & 0xFFu);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const int gi = 8 * it_ch + k;
+                            um = (gi < gs - 1 || gi > gs + 1) ? min(um, gm[k]) : um;
+                        }
+#pragma unroll
+                        for (int o = 1; o < NCH; o <<= 1) um = min(um, __shfl_xor_sync(0xFFFFFFFFu, um, o));
+                    }
+                    if (live && it_ch == 0) { sm.ckey[it_px][0] = best; if (CV) sm.ckey[it_px][1] = um; }
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");  // every prefix entry has been read (the next row may overwrite them); keys and window sums are visible
+                // ---- finishing pass: lane = pixel: winner, neighbours, sub-pixel fraction, output ----
+                if (px_ok) {
+                    const uint32_t best = sm.ckey[px][0];
+                    const uint32_t mv = best >> 8;
+                    const int gs = CV ? 255 - (int)(best & 0xFFu) : (int)(best & 0xFFu);
                     const uint16_t *srow = &sm.sad[px][0];
                     const uint4 v = *reinterpret_cast<const uint4 *>(srow + 8 * gs);
-                    // lowest disparity with SAD == mv inside the group = highest slot
-                    auto sk = [&](uint32_t val, uint32_t k) { return (val << 3) | (7u - k); };
-                    uint32_t bk = __vimin3_u32(sk(v.x & 0xFFFFu, 0), sk(v.x >> 16, 1), sk(v.y & 0xFFFFu, 2));
-                    bk = __vimin3_u32(bk, sk(v.y >> 16, 3), sk(v.z & 0xFFFFu, 4));
-                    bk = __vimin3_u32(bk, sk(v.z >> 16, 5), sk(v.w & 0xFFFFu, 6));
-                    bk = min(bk, sk(v.w >> 16, 7));
-                    const int d1 = 8 * gs + (int)(bk & 7u);            // 7 - k  ==  d - 8g
-                    int L, R;
-                    if (d1 == 0) { uint32_t acc = 0; for (int k = 0; k <= two_h; k++) acc += sm.guard[b][0][px + k]; L = (int)acc; }
-                    else L = srow[slot_of(d1 - 1)];
-                    if (d1 == D - 1) { uint32_t acc = 0; for (int k = 0; k <= two_h; k++) acc += sm.guard[b][1][px + k]; R = (int)acc; }
-                    else R = srow[slot_of(d1 + 1)];
-                    const int q = rtl_frac(L, R, (int)mv);
-                    const int depth = d1 * 256 + q;                    // bm_obuf2.v:122-154
+                    const uint32_t vv[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+                    // slot k <-> d = 8g + 7 - k.  RTL: lowest disparity with SAD == mv = highest slot; OPENCV: highest disparity = lowest slot
+                    uint32_t sk[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sk[k] = (vv[k] << 3) | (CV ? (uint32_t)k : 7u - k);
+                    uint32_t bk = __vimin3_u32(sk[0], sk[1], sk[2]);
+                    bk = __vimin3_u32(bk, sk[3], sk[4]);
+                    bk = __vimin3_u32(bk, sk[5], sk[6]);
+                    bk = min(bk, sk[7]);
+                    const int d1 = 8 * gs + (CV ? 7 - (int)(bk & 7u) : (int)(bk & 7u));
                     int out;
-                    if (depth <= 0) out = -1;
-                    else if (a.rtl_extended) out = depth >> 4;
-                    else out = (int)(int16_t)(((depth >> 4) & 0x0FFF) | ((depth & 0x8000) ? 0xF000 : 0));
+                    if (!CV) {
+                        const uint16_t *gd = reinterpret_cast<const uint16_t *>(&sm.gt[b][0]);        // [d=-1 / d=D][column]
+                        int L, R;
+                        if (d1 == 0) { uint32_t acc = 0; for (int k = 0; k <= two_h; k++) acc += gd[px + k]; L = (int)acc; }
+                        else L = srow[slot_of(d1 - 1)];
+                        if (d1 == D - 1) { uint32_t acc = 0; for (int k = 0; k <= two_h; k++) acc += gd[(U_NC + 8) + px + k]; R = (int)acc; }
+                        else R = srow[slot_of(d1 + 1)];
+                        const int q = rtl_frac(L, R, (int)mv);
+                        const int depth = d1 * 256 + q;                // bm_obuf2.v:122-154
+                        if (depth <= 0) out = -1;
+                        else if (a.rtl_extended) out = depth >> 4;
+                        else out = (int)(int16_t)(((depth >> 4) & 0x0FFF) | ((depth & 0x8000) ? 0xF000 : 0));
+                    } else {
+                        // cv::StereoBM
+                        const int minsad = (int)mv;
+                        bool fail = false;
+                        if (a.uniq > 0) {
+                            // any d with |d - mind| > 1 and SAD(d) <= thresh: the groups away from the winner through their minima (um), the
+                            // winner's group and its two neighbours value by value with mind-1, mind, mind+1 left out
+                            const int thresh = minsad + minsad * a.uniq / 100;
+                            uint32_t umin = sm.ckey[px][1];
+                            const int dl = d1 & 7;                     // position of the winner inside its group
+#pragma unroll
+                            for (int k = 0; k < 8; k++) { const int dk = 7 - k; umin = (dk < dl - 1 || dk > dl + 1) ? min(umin, vv[k]) : umin; }
+                            if (gs > 0) {                              // group below: its top disparity is mind-1 iff the winner sits at the bottom of its group
+                                const uint4 u = *reinterpret_cast<const uint4 *>(srow + 8 * (gs - 1));
+                                const uint32_t top = (dl == 0) ? 0xFFFFu : (u.x & 0xFFFFu);           // slot 0 <-> d = 8(g-1)+7
+                                umin = min(umin, min(min(top, u.x >> 16), min(__vminu2(u.y, __vminu2(u.z, u.w)) & 0xFFFFu, __vminu2(u.y, __vminu2(u.z, u.w)) >> 16)));
+                            }
+                            if (gs < NG - 1) {                         // group above: its bottom disparity is mind+1 iff the winner sits at the top
+                                const uint4 u = *reinterpret_cast<const uint4 *>(srow + 8 * (gs + 1));
+                                const uint32_t bot = (dl == 7) ? 0xFFFFu : (u.w >> 16);               // slot 7 <-> d = 8(g+1)
+                                umin = min(umin, min(min(bot, u.w & 0xFFFFu), min(__vminu2(u.x, __vminu2(u.y, u.z)) & 0xFFFFu, __vminu2(u.x, __vminu2(u.y, u.z)) >> 16)));
+                            }
+                            fail = (int)umin <= thresh;
+                        }
+                        // texture: sum of |L' - cap| over the window = difference of two entries of the column prefix sums
+                        const uint32_t *tx = &sm.gt[b][0];
+                        const uint32_t tsum = tx[px + two_h + 1] - tx[px];
+                        const bool valid = !fail && ((int)tsum >= a.tex_thr);
+                        // neighbours of the winner, mirrored at the ends of the range
+                        const int pp = srow[slot_of(d1 == 0 ? 1 : d1 - 1)], nn = srow[slot_of(d1 == D - 1 ? D - 2 : d1 + 1)];
+                        const int den = pp + nn - 2 * minsad + abs(pp - nn);
+                        // C division toward zero; exact in float: |(pp-nn)*256| < 2^24, den >= 2|pp-nn| so |frac| <= 128, and a
+                        // non-integer quotient is more than 1/den > 2^-18 = half an ulp away from the next integer
+                        const int frac = (den > 0) ? (int)truncf(fdiv_rn_inrange((float)((pp - nn) * 256), (float)den)) : 0;
+                        out = valid ? ((d1 * 256 + frac + 15) >> 4) : -16;
+                        if (a.cost && valid) a.cost[(size_t)f * a.dframe + (size_t)(yb0 + it - (wsz - 1)) * a.dpitch + ctr0 + px] = (int16_t)minsad;
+                    }
                     if (out_x < a.W) *out_p = (int16_t)out;
                 }
             }
@@ -201,7 +270,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
         }
     } else if (warp == CW) {
         // ======================================================================================
-        // staging role: rows of iteration it+1 (newest, oldest) -> shared memory as they are (6-bit masked: lr_din, bm_calc_sad.v:82-101)
+        // staging role: rows of iteration it+1 (newest, oldest) -> shared memory as they are (RTL: 6-bit masked, lr_din, bm_calc_sad.v:82-101)
         // ======================================================================================
         constexpr int RW = RLEN / 4, LW = U_NC / 4, ITEMS = 2 * RW + 2 * LW, NI = (ITEMS + 31) / 32;
         const uint32_t *p[NI]; bool ok0[NI], ok1[NI], on[NI]; int rt[NI], m[NI]; uint32_t so[NI];
@@ -237,7 +306,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             for (int j = 0; j < NI; j++)
                 if (on[j]) {
                     const bool isr = (lane + 32 * j) < 2 * RW;
-                    const uint32_t v = __funnelshift_r(w0r[j], w1r[j], m[j]) & 0x3F3F3F3Fu;
+                    const uint32_t v = __funnelshift_r(w0r[j], w1r[j], m[j]) & (CV ? 0xFFFFFFFFu : 0x3F3F3F3Fu);
                     *reinterpret_cast<uint32_t *>(usm_raw + so[j] + boff * (isr ? RLEN : U_NC)) = v;
                     if (!isr) {                                       // L pixels once more, replicated for the compute threads
                         const uint32_t o4 = (uint32_t)offsetof(SM, lrow4) + 4u * (so[j] - (uint32_t)offsetof(SM, lrow)) + boff * 4u * U_NC;
@@ -255,43 +324,73 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
         }
     } else {
         // ======================================================================================
-        // guard role: column sums of d = -1 and d = D (bm_calc_sad.v lanes 0 and 33), 8 columns per item, column-parallel
+        // guard role.  RTL: column sums of d = -1 and d = D (bm_calc_sad.v lanes 0 and 33), 8 columns per item, column-parallel.
+        // OPENCV: the texture column sums |L' - cap| (cv::StereoBM textureThreshold) and their prefix sums over the tile's columns.
         // ======================================================================================
-        uint4 cg[2];                                                  // item = lane + 32*j: segment = item >> 1, which = item & 1
+        uint4 cg[2];                                                  // RTL: item = lane + 32*j: segment = item >> 1, which = item & 1
         cg[0] = cg[1] = make_uint4(0, 0, 0, 0);
+        const uint32_t cap4 = (uint32_t)a.cap * 0x01010101u;
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         for (int it = 0; it < nsteps; it++) {
             const int b = it & 1;
+            if (CV) {
+                // lane = segment (20 of 32 lanes): 8 columns packed as 4 x u16x2
+                const int s = min(lane, U_NSEG - 1);
+                const uint2 ln = *reinterpret_cast<const uint2 *>(&sm.lrow[b][0][8 * s]);
+                const uint2 lo = *reinterpret_cast<const uint2 *>(&sm.lrow[b][1][8 * s]);
+                const uint32_t an0 = __vabsdiffu4(ln.x, cap4), an1 = __vabsdiffu4(ln.y, cap4);
+                uint4 &cc = cg[0];
+                cc.x += fprmt(an0, 0, 0x4140); cc.y += fprmt(an0, 0, 0x4342); cc.z += fprmt(an1, 0, 0x4140); cc.w += fprmt(an1, 0, 0x4342);
+                if (it >= wsz) {                                      // (before that the oldest row is not part of the window: its staged zeros are not pixels)
+                    const uint32_t ao0 = __vabsdiffu4(lo.x, cap4), ao1 = __vabsdiffu4(lo.y, cap4);
+                    cc.x -= fprmt(ao0, 0, 0x4140); cc.y -= fprmt(ao0, 0, 0x4342); cc.z -= fprmt(ao1, 0, 0x4140); cc.w -= fprmt(ao1, 0, 0x4342);
+                }
+                uint32_t pf[8];                                       // inclusive prefix inside the segment
+                pf[0] = cc.x & 0xFFFFu; pf[1] = pf[0] + (cc.x >> 16); pf[2] = pf[1] + (cc.y & 0xFFFFu); pf[3] = pf[2] + (cc.y >> 16);
+                pf[4] = pf[3] + (cc.z & 0xFFFFu); pf[5] = pf[4] + (cc.z >> 16); pf[6] = pf[5] + (cc.w & 0xFFFFu); pf[7] = pf[6] + (cc.w >> 16);
+                uint32_t tot = (lane < U_NSEG) ? pf[7] : 0u, sc = tot;                    // exclusive scan of the segment totals
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int item = lane + 32 * j;
-                if (item < 2 * U_NSEG) {
-                    const int s = item >> 1, which = item & 1;
-                    uint2 rv[2];
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, sc, o); if (lane >= o) sc += t; }
+                const uint32_t base = sc - tot;
+                if (lane < U_NSEG) {
+                    uint32_t *tx = &sm.gt[b][1 + 8 * s];              // entry 1 + column
 #pragma unroll
-                    for (int t = 0; t < 2; t++) {                     // newest, oldest
-                        if (which) rv[t] = *reinterpret_cast<const uint2 *>(&sm.rrow[b][t][8 * s + 8]);          // R(x - D)
-                        else {                                        // R(x + 1): bytes 1..8 of the pair at 8s+D+8
-                            const uint2 u0 = *reinterpret_cast<const uint2 *>(&sm.rrow[b][t][8 * s + D + 8]);
-                            const uint32_t u2 = (8 * s + D + 16 < RLEN) ? *reinterpret_cast<const uint32_t *>(&sm.rrow[b][t][8 * s + D + 16]) : 0u;
-                            rv[t] = make_uint2(__funnelshift_r(u0.x, u0.y, 8), __funnelshift_r(u0.y, u2, 8));
+                    for (int i = 0; i < 8; i++) tx[i] = base + pf[i];
+                    if (lane == 0) sm.gt[b][0] = 0u;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int item = lane + 32 * j;
+                    if (item < 2 * U_NSEG) {
+                        const int s = item >> 1, which = item & 1;
+                        uint2 rv[2];
+#pragma unroll
+                        for (int t = 0; t < 2; t++) {                 // newest, oldest
+                            if (which) rv[t] = *reinterpret_cast<const uint2 *>(&sm.rrow[b][t][8 * s + 8]);      // R(x - D)
+                            else {                                    // R(x + 1): bytes 1..8 of the pair at 8s+D+8
+                                const uint2 u0 = *reinterpret_cast<const uint2 *>(&sm.rrow[b][t][8 * s + D + 8]);
+                                const uint32_t u2 = (8 * s + D + 16 < RLEN) ? *reinterpret_cast<const uint32_t *>(&sm.rrow[b][t][8 * s + D + 16]) : 0u;
+                                rv[t] = make_uint2(__funnelshift_r(u0.x, u0.y, 8), __funnelshift_r(u0.y, u2, 8));
+                            }
                         }
+                        const uint2 ln = *reinterpret_cast<const uint2 *>(&sm.lrow[b][0][8 * s]);
+                        const uint2 lo = *reinterpret_cast<const uint2 *>(&sm.lrow[b][1][8 * s]);
+                        const uint32_t an0 = __vabsdiffu4(ln.x, rv[0].x), an1 = __vabsdiffu4(ln.y, rv[0].y);
+                        const uint32_t ao0 = __vabsdiffu4(lo.x, rv[1].x), ao1 = __vabsdiffu4(lo.y, rv[1].y);
+                        uint4 &cc = cg[j];
+                        if (SAT) {
+                            cc.x -= __vminu2(cc.x, fprmt(ao0, 0, 0x4140)); cc.y -= __vminu2(cc.y, fprmt(ao0, 0, 0x4342));
+                            cc.z -= __vminu2(cc.z, fprmt(ao1, 0, 0x4140)); cc.w -= __vminu2(cc.w, fprmt(ao1, 0, 0x4342));
+                            cc.x = __viaddmin_u16x2(cc.x, fprmt(an0, 0, 0x4140), 0x03FF03FFu); cc.y = __viaddmin_u16x2(cc.y, fprmt(an0, 0, 0x4342), 0x03FF03FFu);
+                            cc.z = __viaddmin_u16x2(cc.z, fprmt(an1, 0, 0x4140), 0x03FF03FFu); cc.w = __viaddmin_u16x2(cc.w, fprmt(an1, 0, 0x4342), 0x03FF03FFu);
+                        } else {
+                            cc.x += fprmt(an0, 0, 0x4140) - fprmt(ao0, 0, 0x4140); cc.y += fprmt(an0, 0, 0x4342) - fprmt(ao0, 0, 0x4342);
+                            cc.z += fprmt(an1, 0, 0x4140) - fprmt(ao1, 0, 0x4140); cc.w += fprmt(an1, 0, 0x4342) - fprmt(ao1, 0, 0x4342);
+                        }
+                        uint16_t *gd = reinterpret_cast<uint16_t *>(&sm.gt[b][0]) + which * (U_NC + 8);
+                        *reinterpret_cast<uint4 *>(gd + 8 * s) = cc;  // columns 8s .. 8s+7 as u16
                     }
-                    const uint2 ln = *reinterpret_cast<const uint2 *>(&sm.lrow[b][0][8 * s]);
-                    const uint2 lo = *reinterpret_cast<const uint2 *>(&sm.lrow[b][1][8 * s]);
-                    const uint32_t an0 = __vabsdiffu4(ln.x, rv[0].x), an1 = __vabsdiffu4(ln.y, rv[0].y);
-                    const uint32_t ao0 = __vabsdiffu4(lo.x, rv[1].x), ao1 = __vabsdiffu4(lo.y, rv[1].y);
-                    uint4 &cc = cg[j];
-                    if (SAT) {
-                        cc.x -= __vminu2(cc.x, fprmt(ao0, 0, 0x4140)); cc.y -= __vminu2(cc.y, fprmt(ao0, 0, 0x4342));
-                        cc.z -= __vminu2(cc.z, fprmt(ao1, 0, 0x4140)); cc.w -= __vminu2(cc.w, fprmt(ao1, 0, 0x4342));
-                        cc.x = __viaddmin_u16x2(cc.x, fprmt(an0, 0, 0x4140), 0x03FF03FFu); cc.y = __viaddmin_u16x2(cc.y, fprmt(an0, 0, 0x4342), 0x03FF03FFu);
-                        cc.z = __viaddmin_u16x2(cc.z, fprmt(an1, 0, 0x4140), 0x03FF03FFu); cc.w = __viaddmin_u16x2(cc.w, fprmt(an1, 0, 0x4342), 0x03FF03FFu);
-                    } else {
-                        cc.x += fprmt(an0, 0, 0x4140) - fprmt(ao0, 0, 0x4140); cc.y += fprmt(an0, 0, 0x4342) - fprmt(ao0, 0, 0x4342);
-                        cc.z += fprmt(an1, 0, 0x4140) - fprmt(ao1, 0, 0x4140); cc.w += fprmt(an1, 0, 0x4342) - fprmt(ao1, 0, 0x4342);
-                    }
-                    *reinterpret_cast<uint4 *>(&sm.guard[b][which][8 * s]) = cc;             // columns 8s .. 8s+7 as u16
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
@@ -299,18 +398,20 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
     }
 }
 
-template <bool SAT, int NG>
+template <int PROFILE, bool SAT, int NG>
 static inline void fused_go(const FastArgs &a, int n, cudaStream_t s)
 {
     const int smem = (int)sizeof(FusedSmem<NG>);
-    cudaFuncSetAttribute(k_bm_fused<SAT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_bm_fused<SAT, NG><<<dim3(a.ntx_tiles, a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
+    cudaFuncSetAttribute(k_bm_fused<PROFILE, SAT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_bm_fused<PROFILE, SAT, NG><<<dim3(a.ntx_tiles, a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
 }
 
-// RTL profile, 64 / 128 / 256 disparities, uniqueness filter off, window 9..31
+// 64 / 128 / 256 disparities, window 9..31; RTL profile with the uniqueness filter off, or the cv::StereoBM profile
 static inline bool bm_fused_supported(const BmConfig &c)
 {
-    return c.profile == U96_PROFILE_RTL && (c.D == 64 || c.D == 128 || c.D == 256) && !c.uni_enable && c.wsz >= 9 && c.wsz <= 31;
+    if (!(c.D == 64 || c.D == 128 || c.D == 256) || c.wsz < 9 || c.wsz > 31) return false;
+    if (c.profile == U96_PROFILE_RTL) return !c.uni_enable;
+    return c.profile == U96_PROFILE_OPENCV && c.cap >= 1 && c.cap <= 63;
 }
 
 static inline int launch_bm_fused(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,
@@ -321,10 +422,15 @@ static inline int launch_bm_fused(const uint8_t *xl, const uint8_t *xr, int pitc
     const int ng = c.D / 8;
     fast_fill_args<5>(a, c, n, 1, fused_occupancy(ng) * fast_sm_count());    // same tile (160 columns) and valid rectangle as k_bm_fast<NCW=5>
     if (a.ctr_hi < a.ctr_lo || a.y_hi < a.y_lo) return 0;
+    constexpr int R = U96_PROFILE_RTL, V = U96_PROFILE_OPENCV;
+    if (c.profile == U96_PROFILE_OPENCV) {
+        if (ng == 8) fused_go<V, false, 8>(a, n, s); else if (ng == 16) fused_go<V, false, 16>(a, n, s); else fused_go<V, false, 32>(a, n, s);
+        return 1;
+    }
     const bool sat = c.wsz * 63 > 1023;
-    if (ng == 8)       { if (sat) fused_go<true, 8>(a, n, s);  else fused_go<false, 8>(a, n, s); }
-    else if (ng == 16) { if (sat) fused_go<true, 16>(a, n, s); else fused_go<false, 16>(a, n, s); }
-    else               { if (sat) fused_go<true, 32>(a, n, s); else fused_go<false, 32>(a, n, s); }
+    if (ng == 8)       { if (sat) fused_go<R, true, 8>(a, n, s);  else fused_go<R, false, 8>(a, n, s); }
+    else if (ng == 16) { if (sat) fused_go<R, true, 16>(a, n, s); else fused_go<R, false, 16>(a, n, s); }
+    else               { if (sat) fused_go<R, true, 32>(a, n, s); else fused_go<R, false, 32>(a, n, s); }
     return 1;
 }
 
