@@ -40,7 +40,7 @@ WORKLOADS = {
     # name: (W, H, D, block, seed, frames per step per GPU)
     "c2": dict(W=640, H=480, D=64, B=21, seed=1, batch=296, name="C2 synthetic 640x480 D64 B21 raw->rect->xsbl->bm (RTL profile)"),
     "c3": dict(W=1242, H=375, D=128, B=15, seed=2, batch=148, name="C3 KITTI-shape 1242x375 D128 B15 raw->rect->xsbl->bm (RTL profile)"),
-    "c4": dict(W=1920, H=1080, D=256, B=21, seed=3, batch=32, name="C4 1920x1080 D256 B21 raw->rect->xsbl->bm (RTL-extended profile)"),
+    "c4": dict(W=1920, H=1080, D=256, B=21, seed=3, batch=37, name="C4 1920x1080 D256 B21 raw->rect->xsbl->bm (RTL-extended profile)"),
 }
 # survey cross-check values of the RTL profile on the bundled pair -- used by the c1 sub-record
 C1_CRC = {21: "3c312d26", 15: "d0650ea3"}
@@ -498,14 +498,14 @@ def sub_opencv(cx, steps, reps, cv2_threads):
     preFilterCap 31, texture 10, uniqueness 10, disp12MaxDiff 1, speckle 50/32 -- rectified pairs in HOST memory in, 16x disparity
     in HOST memory out (u96_submit_rect_async), next to cv2.StereoBM with the same settings on the same frames in this run."""
     u = cx.u
-    wl = dict(W=640, H=480, D=64, B=21, seed=1, batch=256)
-    pool = 64
+    wl = dict(W=640, H=480, D=64, B=21, seed=1, batch=296)
+    pool = 74
     mine = shard_frames(pool * cx.world, cx.rank, cx.world)
     pairs = [u.synth_pair(1, i, 640, 480, 64) for i in mine]
-    hL = np.concatenate([np.stack([p[0] for p in pairs])] * 4); hR = np.concatenate([np.stack([p[1] for p in pairs])] * 4)
+    hL = np.concatenate([np.stack([p[0] for p in pairs])] * 4); hR = np.concatenate([np.stack([p[1] for p in pairs])] * 4)      # 296 = 2 full waves of the BM grid
     m = measure(cx, wl, hL, hR, profile=u.PROFILE_OPENCV, entry="rect", steps=steps, warmup=2, reps=reps, bm_extra=MAINCPP, e2e=True, e2e_reps=3)
-    rec = {"workload": "cv::StereoBM profile + validateDisparity + filterSpeckles (main.cpp:198-212), 640x480 D64 B21, 256 rectified pairs per step "
-                       "from a 64-frame pool, host buffers in and out",
+    rec = {"workload": "cv::StereoBM profile + validateDisparity + filterSpeckles (main.cpp:198-212), 640x480 D64 B21, 296 rectified pairs per step "
+                       "from a 74-frame pool, host buffers in and out",
            "value": m["value"], "ms_per_step": m["ms_per_step"], "e2e": m["e2e"]["value"], "e2e_spread": m["e2e"]["spread"],
            "kernel_ms": m["stage_ms_per_step"]["bm"], "postfilter_ms": m["stage_ms_per_step"]["post"], "xsbl_ms": m["stage_ms_per_step"]["xsbl"],
            "roofline_frac": m.get("bm_roofline", {}).get("frac"), "gpu_launches": m["gpu_launches"]}

@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                 //      bm_calc_det.v / bm_calc_upd.v strict <) or 255 - group (OPENCV: the higher one, reverse scan) ----
                 {
                     const bool live = it_px < ntx;
-                    const uint32_t *pm = &sm.pmin[(live ? it_px : 0) >> 3][NG * ((live ? it_px : 0) & 7) + 8 * it_ch];
+                    const int rp = live ? it_px : warp * (32 >> LG) * 8;       // idle lanes re-read a row of their own warp (their result is dropped)
+                    const uint32_t *pm = &sm.pmin[rp >> 3][NG * (rp & 7) + 8 * it_ch];
                     const uint4 pa = *reinterpret_cast<const uint4 *>(pm), pb = *reinterpret_cast<const uint4 *>(pm + 4);
                     const uint32_t m8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
                     uint32_t gm[8], key[8];
