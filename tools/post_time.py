@@ -12,7 +12,7 @@ import u96_slam_b200 as u  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 W, H, D = 640, 480, 64
 L, R = u.synth_batch(1, 0, 16, W, H, D)
-hL = np.concatenate([L] * (n // 16)); hR = np.concatenate([R] * (n // 16))
+hL = np.concatenate([L] * ((n + 15) // 16))[:n]; hR = np.concatenate([R] * ((n + 15) // 16))[:n]
 fe = u.StereoFrontEnd(0, W, H, n)
 fe.set_bm_params(width=W, height=H, profile=1, block_size=21, num_disparities=D, prefilter_cap=31, texture_threshold=10, uniqueness_ratio=10,
                  disp12_max_diff=1, speckle_window_size=50, speckle_range=32)
