@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                         const uint32_t ao0 = __vabsdiffu4(lo.x, rv[1].x), ao1 = __vabsdiffu4(lo.y, rv[1].y);
                         uint4 &cc = cg[j];
                         if (SAT) {
-                            cc.x -= __vminu2(cc.x, fprmt(ao0, 0, 0x4140)); cc.y -= __vminu2(cc.y, fprmt(ao0, 0, 0x4342));
-                            cc.z -= __vminu2(cc.z, fprmt(ao1, 0, 0x4140)); cc.w -= __vminu2(cc.w, fprmt(ao1, 0, 0x4342));
+                            cc.x = satsub_u16x2(cc.x, fprmt(ao0, 0, 0x4140)); cc.y = satsub_u16x2(cc.y, fprmt(ao0, 0, 0x4342));
+                            cc.z = satsub_u16x2(cc.z, fprmt(ao1, 0, 0x4140)); cc.w = satsub_u16x2(cc.w, fprmt(ao1, 0, 0x4342));
                             cc.x = __viaddmin_u16x2(cc.x, fprmt(an0, 0, 0x4140), 0x03FF03FFu); cc.y = __viaddmin_u16x2(cc.y, fprmt(an0, 0, 0x4342), 0x03FF03FFu);
                             cc.z = __viaddmin_u16x2(cc.z, fprmt(an1, 0, 0x4140), 0x03FF03FFu); cc.w = __viaddmin_u16x2(cc.w, fprmt(an1, 0, 0x4342), 0x03FF03FFu);
                         } else {
