@@ -33,22 +33,40 @@ namespace u96 {
 
 constexpr int U_NC = 160, U_NSEG = 20;                 // tile columns, segments of 8 columns
 
-template <int NG>
+#ifndef U96_FUSED_WIDE
+#define U96_FUSED_WIDE 1                   // 0: the saturating RTL variants use the byte rows + PRMT widening of the other variants
+#endif
+
+// WIDE (the saturating RTL variants): the staged R rows are 16-bit per pixel, so the 8-disparity window of a column is four words
+// already in the 2 x u16 lane format of the column sums -- aligned words for the odd columns of a segment, and for the even ones
+// seven 16-bit funnel shifts shared by all four of them: no PRMT widening (64 per row and thread) on the ALU pipe, which binds
+// this step, and the oldest row's |l - r| and saturating subtract run on the FMA pipe as fp16 (satsub_absdiff_u16x2).
+template <int NG, bool WIDE>
 struct FusedSmem {
-    static constexpr int D = 8 * NG, RLEN = U_NC + D + 16, SADP = D + 8, PMS = 9 * NG, NCH = NG / 8;
+    static constexpr int D = 8 * NG, RLEN = U_NC + D + 16, RB = WIDE ? 2 * RLEN : RLEN, SADP = D + 8, PMS = 9 * NG, NCH = NG / 8;
+    // pixels / segments with window sums: a saturating window is at least 17 wide, so a tile holds at most 144 pixels there
+    static constexpr int NPX = WIDE ? 144 : U_NC, NPS = NPX / 8;
     uint4 pre[U_NC + 8][NG];               // inclusive prefix sums inside a segment: [column][group] = 8 x u16; 8 never-written pad columns: the
                                            // unrolled sweep of the last segment reads up to 7 columns past the tile for pixels nobody finishes
-    uint16_t sad[U_NC][SADP];              // window sums of the row in flight; pitch 2D+16 B: rows skew over the banks
-    uint32_t pmin[U_NSEG][PMS];            // packed minima [segment][pixel j][group] (odd | even disparities); 9*NG-word segment stride: the
+    uint16_t sad[NPX][SADP];               // window sums of the row in flight; pitch 2D+16 B: rows skew over the banks
+    uint32_t pmin[NPS][PMS];            // packed minima [segment][pixel j][group] (odd | even disparities); 9*NG-word segment stride: the
                                            // segments of a warp store to disjoint banks
-    uint32_t ckey[U_NC][2];                // per pixel: winner key (min SAD << 8 | group code) and, OPENCV, the smallest group minimum outside the
+    uint32_t ckey[NPX][WIDE ? 1 : 2];     // per pixel: winner key (min SAD << 8 | group code) and, OPENCV, the smallest group minimum outside the
                                            // winner's group and its two neighbours
     uint32_t gt[2][U_NC + 8];              // output of the guard warp, [buffer]: RTL = u16 [d=-1 / d=D][column] column sums of the guard lanes;
                                            // OPENCV = u32 [1 + column] prefix sums over the columns of the texture column sums (entry 0 = 0)
-    uint8_t rrow[2][2][RLEN];              // [buffer][newest / oldest] R row segment: R[xs - D - 8 .. xs + 168)
-    uint32_t lrow4[2][2][U_NC];            // L row segment, every pixel replicated into the four bytes of a word (VABSDIFF4 operand)
+    uint8_t rrow[2][2][RB];                // [buffer][newest / oldest] R row segment: R[xs - D - 8 .. xs + 168); WIDE: u16 per pixel
+    uint32_t lrow4[2][2][U_NC];            // L row segment, every pixel replicated into the four bytes of a word (VABSDIFF4 operand); WIDE: into its two halves
     uint8_t lrow[2][2][U_NC];              // L row segment (guard warp: 8 columns per word pair)
 };
+
+// |l - r| on two u16 lanes below 2048 and max(c - |l - r|, 0), both on the FMA pipe (see satsub_u16x2): HADD2 + HADD2.SAT with -|.| folded
+__device__ __forceinline__ uint32_t satsub_absdiff_u16x2(uint32_t c, uint32_t l, uint32_t r)
+{
+    uint32_t d;
+    asm("{\n\t.reg .b32 t, u;\n\tsub.f16x2 t, %2, %3;\n\tabs.f16x2 u, t;\n\tsub.sat.f16x2 %0, %1, u;\n\t}" : "=r"(d) : "r"(c), "r"(l), "r"(r));
+    return d;
+}
 
 // bytes (i+1)..(i+8) of the 16-byte pair (a, b): the R window of column i of a segment (i = 7: b itself)
 __device__ __forceinline__ uint2 r_window(uint2 a, uint2 b, int i)
@@ -70,8 +88,9 @@ template <int PROFILE, bool SAT, int NG>
 __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fused(const FastArgs a)
 {
     constexpr bool CV = (PROFILE == U96_PROFILE_OPENCV);
-    using SM = FusedSmem<NG>;
-    constexpr int D = SM::D, RLEN = SM::RLEN, SADP = SM::SADP, NCH = SM::NCH;
+    constexpr bool WIDE = U96_FUSED_WIDE && !CV && SAT;
+    using SM = FusedSmem<NG, WIDE>;
+    constexpr int D = SM::D, RLEN = SM::RLEN, RB = SM::RB, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
     constexpr int LG = (NG == 8) ? 3 : (NG == 16) ? 4 : 5;
     extern __shared__ __align__(16) unsigned char usm_raw[];
@@ -117,7 +136,45 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             const int b = it & 1;
             uint4 run;                                                // prefix sums of the 8 columns; after phase 1: the block sum
             // ---- phase 1: the newest and the oldest row enter the 64 column sums of this thread ----
-            {
+            if constexpr (WIDE) {
+                // oldest row first, on the FMA pipe: c = max(c - |l - r|, 0); then the newest row on the ALU pipe: c = min(c + |l - r|, 1023)
+                uint4 *prow = &sm.pre[8 * s][g];
+                {
+                    const uint4 *E = reinterpret_cast<const uint4 *>(&sm.rrow[b][1][2 * aoff]);
+                    const uint4 e0 = E[0], e1 = E[1];
+                    const uint4 la = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][1][8 * s]), lb = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][1][8 * s + 4]);
+                    const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    uint32_t ow[7];                                   // one pixel ahead: halves 1..14
+#pragma unroll
+                    for (int k = 0; k < 7; k++) ow[k] = __funnelshift_r(ew[k], ew[k + 1], 16);
+                    const uint32_t lw[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t *w = (i & 1) ? &ew[(i + 1) >> 1] : &ow[i >> 1];
+                        c[i].x = satsub_absdiff_u16x2(c[i].x, lw[i], w[0]); c[i].y = satsub_absdiff_u16x2(c[i].y, lw[i], w[1]);
+                        c[i].z = satsub_absdiff_u16x2(c[i].z, lw[i], w[2]); c[i].w = satsub_absdiff_u16x2(c[i].w, lw[i], w[3]);
+                    }
+                }
+                {
+                    const uint4 *E = reinterpret_cast<const uint4 *>(&sm.rrow[b][0][2 * aoff]);
+                    const uint4 e0 = E[0], e1 = E[1];
+                    const uint4 la = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][0][8 * s]), lb = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][0][8 * s + 4]);
+                    const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    uint32_t ow[7];                                   // one pixel ahead: halves 1..14
+#pragma unroll
+                    for (int k = 0; k < 7; k++) ow[k] = __funnelshift_r(ew[k], ew[k + 1], 16);
+                    const uint32_t lw[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+                    run = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t *w = (i & 1) ? &ew[(i + 1) >> 1] : &ow[i >> 1];
+                        c[i].x = __viaddmin_u16x2(c[i].x, __vabsdiffu4(lw[i], w[0]), 0x03FF03FFu); c[i].y = __viaddmin_u16x2(c[i].y, __vabsdiffu4(lw[i], w[1]), 0x03FF03FFu);
+                        c[i].z = __viaddmin_u16x2(c[i].z, __vabsdiffu4(lw[i], w[2]), 0x03FF03FFu); c[i].w = __viaddmin_u16x2(c[i].w, __vabsdiffu4(lw[i], w[3]), 0x03FF03FFu);
+                        run.x += c[i].x; run.y += c[i].y; run.z += c[i].z; run.w += c[i].w;
+                        prow[NG * i] = run;
+                    }
+                }
+            } else {
                 const uint4 ln_a = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][0][8 * s]), ln_b = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][0][8 * s + 4]);
                 const uint4 lo_a = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][1][8 * s]), lo_b = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][1][8 * s + 4]);
                 const uint32_t lnw[8] = {ln_a.x, ln_a.y, ln_a.z, ln_a.w, ln_b.x, ln_b.y, ln_b.z, ln_b.w};
@@ -165,9 +222,10 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                 //      bm_calc_det.v / bm_calc_upd.v strict <) or 255 - group (OPENCV: the higher one, reverse scan) ----
                 {
                     const bool live = it_px < ntx;
-                    const int rp = live ? it_px : warp * (32 >> LG) * 8;       // idle lanes re-read a row of their own warp (their result is dropped)
+                    const int rp = live ? it_px : 0;                           // idle lanes load nothing (their result is dropped)
                     const uint32_t *pm = &sm.pmin[rp >> 3][NG * (rp & 7) + 8 * it_ch];
-                    const uint4 pa = *reinterpret_cast<const uint4 *>(pm), pb = *reinterpret_cast<const uint4 *>(pm + 4);
+                    const uint4 none = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    const uint4 pa = live ? *reinterpret_cast<const uint4 *>(pm) : none, pb = live ? *reinterpret_cast<const uint4 *>(pm + 4) : none;
                     const uint32_t m8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
                     uint32_t gm[8], key[8];
 #pragma unroll
@@ -194,7 +252,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
 #pragma unroll
                         for (int o = 1; o < NCH; o <<= 1) um = min(um, __shfl_xor_sync(0xFFFFFFFFu, um, o));
                     }
-                    if (live && it_ch == 0) { sm.ckey[it_px][0] = best; if (CV) sm.ckey[it_px][1] = um; }
+                    if (live && it_ch == 0) { sm.ckey[it_px][0] = best; if (CV) sm.ckey[it_px][CV ? 1 : 0] = um; }
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");  // every prefix entry has been read (the next row may overwrite them); keys and window sums are visible
                 // ---- finishing pass: lane = pixel: winner, neighbours, sub-pixel fraction, output ----
@@ -235,7 +293,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                             // any d with |d - mind| > 1 and SAD(d) <= thresh: the groups away from the winner through their minima (um), the
                             // winner's group and its two neighbours value by value with mind-1, mind, mind+1 left out
                             const int thresh = minsad + minsad * a.uniq / 100;
-                            uint32_t umin = sm.ckey[px][1];
+                            uint32_t umin = sm.ckey[px][CV ? 1 : 0];
                             const int dl = d1 & 7;                     // position of the winner inside its group
 #pragma unroll
                             for (int k = 0; k < 8; k++) { const int dk = 7 - k; umin = (dk < dl - 1 || dk > dl + 1) ? min(umin, vv[k]) : umin; }
@@ -288,7 +346,8 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             m[j] = (x0 & 3) * 8;
             ok0[j] = on[j] && w0 >= 0 && w0 < pw; ok1[j] = on[j] && w0 + 1 >= 0 && w0 + 1 < pw;
             p[j] = reinterpret_cast<const uint32_t *>(isr ? gr : gl) + ((ptrdiff_t)(yb0 - h - (rt[j] ? wsz : 0)) * pw + w0);
-            so[j] = (uint32_t)((isr ? offsetof(SM, rrow) + (size_t)rt[j] * RLEN : offsetof(SM, lrow) + (size_t)rt[j] * U_NC) + 4 * q);
+            so[j] = (uint32_t)((isr ? offsetof(SM, rrow) + (size_t)rt[j] * RB + (WIDE ? 8 : 4) * q : offsetof(SM, lrow) + (size_t)rt[j] * U_NC + 4 * q));
+
         }
         uint32_t w0r[NI], w1r[NI];
         auto load = [&](int it) {
@@ -308,11 +367,16 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                 if (on[j]) {
                     const bool isr = (lane + 32 * j) < 2 * RW;
                     const uint32_t v = __funnelshift_r(w0r[j], w1r[j], m[j]) & (CV ? 0xFFFFFFFFu : 0x3F3F3F3Fu);
-                    *reinterpret_cast<uint32_t *>(usm_raw + so[j] + boff * (isr ? RLEN : U_NC)) = v;
+                    unsigned char *dst = usm_raw + so[j] + boff * (isr ? RB : U_NC);
+                    if (WIDE && isr) {
+                        *reinterpret_cast<uint2 *>(dst) = make_uint2(fprmt(v, 0, 0x4140), fprmt(v, 0, 0x4342));       // pixels 4q .. 4q+3 as u16
+                    } else {
+                        *reinterpret_cast<uint32_t *>(dst) = v;
+                    }
                     if (!isr) {                                       // L pixels once more, replicated for the compute threads
+                        constexpr uint32_t REP = WIDE ? 0x00010001u : 0x01010101u;
                         const uint32_t o4 = (uint32_t)offsetof(SM, lrow4) + 4u * (so[j] - (uint32_t)offsetof(SM, lrow)) + boff * 4u * U_NC;
-                        *reinterpret_cast<uint4 *>(usm_raw + o4) = make_uint4((v & 0xFFu) * 0x01010101u, ((v >> 8) & 0xFFu) * 0x01010101u,
-                                                                              ((v >> 16) & 0xFFu) * 0x01010101u, (v >> 24) * 0x01010101u);
+                        *reinterpret_cast<uint4 *>(usm_raw + o4) = make_uint4((v & 0xFFu) * REP, ((v >> 8) & 0xFFu) * REP, ((v >> 16) & 0xFFu) * REP, (v >> 24) * REP);
                     }
                 }
         };
@@ -365,6 +429,27 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                     const int item = lane + 32 * j;
                     if (item < 2 * U_NSEG) {
                         const int s = item >> 1, which = item & 1;
+                        uint4 &cc = cg[j];
+                        uint16_t *gd = reinterpret_cast<uint16_t *>(&sm.gt[b][0]) + which * (U_NC + 8);
+                        if constexpr (WIDE) {
+                            // R(x - D): halves 8s+8 ..; R(x + 1): halves 8s+D+9 .. (one pixel past an aligned quad); L pairs widened here
+                            const uint2 ln = *reinterpret_cast<const uint2 *>(&sm.lrow[b][0][8 * s]);
+                            const uint2 lo = *reinterpret_cast<const uint2 *>(&sm.lrow[b][1][8 * s]);
+                            const int ro = which ? 2 * (8 * s + 8) : 2 * (8 * s + D + 8);
+                            uint4 rn = *reinterpret_cast<const uint4 *>(&sm.rrow[b][0][ro]), rold = *reinterpret_cast<const uint4 *>(&sm.rrow[b][1][ro]);
+                            if (!which) {
+                                const uint32_t tn = *reinterpret_cast<const uint32_t *>(&sm.rrow[b][0][ro + 16]), to = *reinterpret_cast<const uint32_t *>(&sm.rrow[b][1][ro + 16]);
+                                rn = make_uint4(__funnelshift_r(rn.x, rn.y, 16), __funnelshift_r(rn.y, rn.z, 16), __funnelshift_r(rn.z, rn.w, 16), __funnelshift_r(rn.w, tn, 16));
+                                rold = make_uint4(__funnelshift_r(rold.x, rold.y, 16), __funnelshift_r(rold.y, rold.z, 16), __funnelshift_r(rold.z, rold.w, 16), __funnelshift_r(rold.w, to, 16));
+                            }
+                            cc.x = satsub_absdiff_u16x2(cc.x, fprmt(lo.x, 0, 0x4140), rold.x); cc.y = satsub_absdiff_u16x2(cc.y, fprmt(lo.x, 0, 0x4342), rold.y);
+                            cc.z = satsub_absdiff_u16x2(cc.z, fprmt(lo.y, 0, 0x4140), rold.z); cc.w = satsub_absdiff_u16x2(cc.w, fprmt(lo.y, 0, 0x4342), rold.w);
+                            cc.x = __viaddmin_u16x2(cc.x, __vabsdiffu4(fprmt(ln.x, 0, 0x4140), rn.x), 0x03FF03FFu);
+                            cc.y = __viaddmin_u16x2(cc.y, __vabsdiffu4(fprmt(ln.x, 0, 0x4342), rn.y), 0x03FF03FFu);
+                            cc.z = __viaddmin_u16x2(cc.z, __vabsdiffu4(fprmt(ln.y, 0, 0x4140), rn.z), 0x03FF03FFu);
+                            cc.w = __viaddmin_u16x2(cc.w, __vabsdiffu4(fprmt(ln.y, 0, 0x4342), rn.w), 0x03FF03FFu);
+                            *reinterpret_cast<uint4 *>(gd + 8 * s) = cc;
+                        } else {
                         uint2 rv[2];
 #pragma unroll
                         for (int t = 0; t < 2; t++) {                 // newest, oldest
@@ -379,7 +464,6 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                         const uint2 lo = *reinterpret_cast<const uint2 *>(&sm.lrow[b][1][8 * s]);
                         const uint32_t an0 = __vabsdiffu4(ln.x, rv[0].x), an1 = __vabsdiffu4(ln.y, rv[0].y);
                         const uint32_t ao0 = __vabsdiffu4(lo.x, rv[1].x), ao1 = __vabsdiffu4(lo.y, rv[1].y);
-                        uint4 &cc = cg[j];
                         if (SAT) {
                             cc.x = satsub_u16x2(cc.x, fprmt(ao0, 0, 0x4140)); cc.y = satsub_u16x2(cc.y, fprmt(ao0, 0, 0x4342));
                             cc.z = satsub_u16x2(cc.z, fprmt(ao1, 0, 0x4140)); cc.w = satsub_u16x2(cc.w, fprmt(ao1, 0, 0x4342));
@@ -389,8 +473,8 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                             cc.x += fprmt(an0, 0, 0x4140) - fprmt(ao0, 0, 0x4140); cc.y += fprmt(an0, 0, 0x4342) - fprmt(ao0, 0, 0x4342);
                             cc.z += fprmt(an1, 0, 0x4140) - fprmt(ao1, 0, 0x4140); cc.w += fprmt(an1, 0, 0x4342) - fprmt(ao1, 0, 0x4342);
                         }
-                        uint16_t *gd = reinterpret_cast<uint16_t *>(&sm.gt[b][0]) + which * (U_NC + 8);
                         *reinterpret_cast<uint4 *>(gd + 8 * s) = cc;  // columns 8s .. 8s+7 as u16
+                        }
                     }
                 }
             }
@@ -402,7 +486,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
 template <int PROFILE, bool SAT, int NG>
 static inline void fused_go(const FastArgs &a, int n, cudaStream_t s)
 {
-    const int smem = (int)sizeof(FusedSmem<NG>);
+    const int smem = (int)sizeof(FusedSmem<NG, U96_FUSED_WIDE && PROFILE == U96_PROFILE_RTL && SAT>);
     cudaFuncSetAttribute(k_bm_fused<PROFILE, SAT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k_bm_fused<PROFILE, SAT, NG><<<dim3(a.ntx_tiles, a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
 }
@@ -429,6 +513,7 @@ static inline int launch_bm_fused(const uint8_t *xl, const uint8_t *xr, int pitc
         return 1;
     }
     const bool sat = c.wsz * 63 > 1023;
+    if (sat && a.TX > 144) return 0;                                             // cannot happen (window >= 17): FusedSmem::NPX
     if (ng == 8)       { if (sat) fused_go<R, true, 8>(a, n, s);  else fused_go<R, false, 8>(a, n, s); }
     else if (ng == 16) { if (sat) fused_go<R, true, 16>(a, n, s); else fused_go<R, false, 16>(a, n, s); }
     else               { if (sat) fused_go<R, true, 32>(a, n, s); else fused_go<R, false, 32>(a, n, s); }
