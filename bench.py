@@ -697,7 +697,7 @@ def main():
                    "b15": single_pair_latency(cx, 640, 480, 64, 15, u.SHIPPED_RECT_PARAMS)}
         except Exception as e:
             cfg_err["aux"] = f"{type(e).__name__}: {e}"
-        # ---- roofline of the dominant kernel (k_bm_fast): integer pipe by the SURVEY 8(d) convention, measured issue rate as the peak ----
+        # ---- roofline of the dominant kernel (k_bm_fused<RTL, saturating, 64 disparities>): integer pipe by the SURVEY 8(d) convention, measured issue rate as the peak ----
         stage = head["stage_ms_per_step"]
         bmr = head["bm_roofline"]
         peaks = {}
@@ -718,7 +718,7 @@ def main():
         except (OSError, TypeError):
             pass
         bm_ms = stage["bm"]
-        roofline = {"kernel": "k_bm_fast", "bound": "int", "achieved": bmr["achieved"], "peak": bmr["peak"], "unit": "Tlaneop/s",
+        roofline = {"kernel": "k_bm_fused<RTL,SAT,8>", "bound": "int", "achieved": bmr["achieved"], "peak": bmr["peak"], "unit": "Tlaneop/s",
                     "frac": bmr["frac"],
                     "peak_source": "measured live: u96_microbench VABSDIFF4 issue rate (ALU pipe, 64 lanes/clk/SM); "
                                    "MEASURED_PEAKS.json has no integer figure",

@@ -33,6 +33,12 @@ namespace u96 {
 
 constexpr int U_NC = 160, U_NSEG = 20;                 // tile columns, segments of 8 columns
 
+#ifndef U96_FUSED_PF
+#define U96_FUSED_PF -1                    // window-sum step: prefix entries fetched this many pixels ahead (0: in place; -1: per variant, measured)
+#endif
+#ifndef U96_FUSED_KEEP
+#define U96_FUSED_KEEP 1                   // 64 disparities: the winner key and the winner's group stay in registers across the second barrier
+#endif
 #ifndef U96_FUSED_WIDE
 #define U96_FUSED_WIDE 1                   // 0: the saturating RTL variants use the byte rows + PRMT widening of the other variants
 #endif
@@ -89,6 +95,9 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
 {
     constexpr bool CV = (PROFILE == U96_PROFILE_OPENCV);
     constexpr bool WIDE = U96_FUSED_WIDE && !CV && SAT;
+    constexpr bool KEEP = U96_FUSED_KEEP && NG == 8;
+    // same-box A/B (profiles/r02_summary.md): the 72-register variants without the wide rows lose 4 % to a two-pixel look-ahead
+    constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? (WIDE ? 2 : 0) : (NG == 16) ? 2 : 1;
     using SM = FusedSmem<NG, WIDE>;
     constexpr int D = SM::D, RLEN = SM::RLEN, RB = SM::RB, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
@@ -127,11 +136,18 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
         const int it_px = (warp * (32 >> LG) * 8) + (lane / NCH), it_ch = lane % NCH;
         // finishing pass: lane = pixel, on the first five compute warps
         const int px = 32 * warp + lane;
-        const bool px_ok = (warp < 5) && (px < ntx);
         const int out_x = ctr0 + px + (CV ? 0 : a.x_store_offset);
+        const bool px_ok = (warp < 5) && (px < ntx) && (out_x < a.W);          // (the RTL's store offset can push the last pixel of a row out of the image)
         int16_t *out_p = gout + (ptrdiff_t)(yb0 - (wsz - 1)) * (ptrdiff_t)a.dpitch + out_x;   // row of iteration 0 (not dereferenced before wsz-1)
 
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");        // rows of iteration 0 are staged
+        uint4 pf_e0, pf_e1, pf_la, pf_lb;                             // WIDE: oldest-row operands of the coming iteration
+        auto prefetch_old = [&](int bb) {
+            const uint4 *E = reinterpret_cast<const uint4 *>(&sm.rrow[bb][1][2 * aoff]);
+            pf_e0 = E[0]; pf_e1 = E[1];
+            pf_la = *reinterpret_cast<const uint4 *>(&sm.lrow4[bb][1][8 * s]); pf_lb = *reinterpret_cast<const uint4 *>(&sm.lrow4[bb][1][8 * s + 4]);
+        };
+        if (WIDE) prefetch_old(0);
         for (int it = 0; it < nsteps; it++) {
             const int b = it & 1;
             uint4 run;                                                // prefix sums of the 8 columns; after phase 1: the block sum
@@ -140,9 +156,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                 // oldest row first, on the FMA pipe: c = max(c - |l - r|, 0); then the newest row on the ALU pipe: c = min(c + |l - r|, 1023)
                 uint4 *prow = &sm.pre[8 * s][g];
                 {
-                    const uint4 *E = reinterpret_cast<const uint4 *>(&sm.rrow[b][1][2 * aoff]);
-                    const uint4 e0 = E[0], e1 = E[1];
-                    const uint4 la = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][1][8 * s]), lb = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][1][8 * s + 4]);
+                    const uint4 e0 = pf_e0, e1 = pf_e1, la = pf_la, lb = pf_lb;
                     const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
                     uint32_t ow[7];                                   // one pixel ahead: halves 1..14
 #pragma unroll
@@ -195,28 +209,40 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                 // ---- phase 2: window sums of this segment's 8 pixels for this thread's 8 disparities ----
                 if (seg_px) {
                     // W(j) = own block sum - own columns before j  +  whole blocks s+1 .. s+Q(j)-1  +  prefix entry of column 8s+j+2h
-                    uint4 bs = run;
-                    for (int t = 1; t < q0; t++) {
-                        const uint4 v = sm.pre[8 * (s + t) + 7][g];
-                        bs.x += v.x; bs.y += v.y; bs.z += v.z; bs.w += v.w;
-                    }
-                    uint4 bq = make_uint4(0, 0, 0, 0);                // block s+q0: joins at pixel jt (the windows from there on reach past it)
-                    if (jt < 8) bq = sm.pre[8 * (s + q0) + 7][g];
+                    // every load is issued ahead of its use: shared loads do not move above the shared stores of the pixel before,
+                    // and one load in flight per warp leaves the warp waiting on the scoreboard (ncu: 11 % of the kernel's samples)
                     const uint4 *pe = &sm.pre[8 * s + two_h][g];      // prefix entry of the window's last column, pixel j: pe[NG*j]
+                    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+                    uint4 e = zero4, e1 = zero4;
+                    if (PF >= 1) e = pe[0];
+                    if (PF >= 2) e1 = pe[NG];
+                    const uint4 v1 = (q0 > 1) ? sm.pre[8 * (s + 1) + 7][g] : zero4;          // whole blocks s+1 .. s+q0-1 (window <= 31: at most two)
+                    const uint4 v2 = (q0 > 2) ? sm.pre[8 * (s + 2) + 7][g] : zero4;
+                    const uint4 bq = (jt < 8) ? sm.pre[8 * (s + q0) + 7][g] : zero4;         // block s+q0: joins at pixel jt (the windows from there on reach past it)
+                    uint4 bs = run;
+                    if (q0 > 1) { bs.x += v1.x; bs.y += v1.y; bs.z += v1.z; bs.w += v1.w; }
+                    if (q0 > 2) { bs.x += v2.x; bs.y += v2.y; bs.z += v2.z; bs.w += v2.w; }
                     uint16_t *sp = &sm.sad[8 * s][8 * g];
                     uint32_t *mp = &sm.pmin[s][g];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        const uint4 e = pe[NG * j];
+                        uint4 e2 = zero4;
+                        if (PF == 0) e = pe[NG * j];
+                        if (PF == 1 && j + 1 < 8) e1 = pe[NG * (j + 1)];
+                        if (PF == 2 && j + 2 < 8) e2 = pe[NG * (j + 2)];
                         if (j == jt) { bs.x += bq.x; bs.y += bq.y; bs.z += bq.z; bs.w += bq.w; }
                         uint4 w;
                         w.x = bs.x + e.x; w.y = bs.y + e.y; w.z = bs.z + e.z; w.w = bs.w + e.w;
                         *reinterpret_cast<uint4 *>(sp + j * SADP) = w;
                         mp[NG * j] = __vminu2(__vminu2(w.x, w.y), __vminu2(w.z, w.w));       // low half: odd d, high half: even d
                         bs.x -= c[j].x; bs.y -= c[j].y; bs.z -= c[j].z; bs.w -= c[j].w;      // next pixel starts one column later
+                        if (PF >= 1) e = e1;
+                        if (PF >= 2) e1 = e2;
                     }
                 }
                 __syncwarp();
+                uint32_t best_r = 0, um_r = 0;                        // NG == 8: the chunk-pass lane is the finishing lane of the same pixel
+                uint4 v_r = make_uint4(0, 0, 0, 0);
                 // ---- chunk pass (warp-local, lane = (pixel, 64-disparity chunk)): 8 packed minima -> the chunk's key; the NCH lanes of
                 //      a pixel then agree on the winner by shuffles.  Group code = group (RTL: the lower disparity wins a tie,
                 //      bm_calc_det.v / bm_calc_upd.v strict <) or 255 - group (OPENCV: the higher one, reverse scan) ----
@@ -252,16 +278,21 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
 #pragma unroll
                         for (int o = 1; o < NCH; o <<= 1) um = min(um, __shfl_xor_sync(0xFFFFFFFFu, um, o));
                     }
-                    if (live && it_ch == 0) { sm.ckey[it_px][0] = best; if (CV) sm.ckey[it_px][CV ? 1 : 0] = um; }
+                    if (KEEP) {
+                        // window sums and keys of a warp's 32 pixels come from the warp itself: the winner's group is fetched before the barrier
+                        best_r = best; um_r = um;
+                        const int gs = CV ? 255 - (int)(best & 0xFFu) : (int)(best & 0xFFu);
+                        if (live) v_r = *reinterpret_cast<const uint4 *>(&sm.sad[it_px][8 * gs]);
+                    } else if (live && it_ch == 0) { sm.ckey[it_px][0] = best; if (CV) sm.ckey[it_px][CV ? 1 : 0] = um; }
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");  // every prefix entry has been read (the next row may overwrite them); keys and window sums are visible
                 // ---- finishing pass: lane = pixel: winner, neighbours, sub-pixel fraction, output ----
                 if (px_ok) {
-                    const uint32_t best = sm.ckey[px][0];
+                    const uint32_t best = KEEP ? best_r : sm.ckey[px][0];
                     const uint32_t mv = best >> 8;
                     const int gs = CV ? 255 - (int)(best & 0xFFu) : (int)(best & 0xFFu);
                     const uint16_t *srow = &sm.sad[px][0];
-                    const uint4 v = *reinterpret_cast<const uint4 *>(srow + 8 * gs);
+                    const uint4 v = KEEP ? v_r : *reinterpret_cast<const uint4 *>(srow + 8 * gs);
                     const uint32_t vv[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
                     // slot k <-> d = 8g + 7 - k.  RTL: lowest disparity with SAD == mv = highest slot; OPENCV: highest disparity = lowest slot
                     uint32_t sk[8];
@@ -293,7 +324,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                             // any d with |d - mind| > 1 and SAD(d) <= thresh: the groups away from the winner through their minima (um), the
                             // winner's group and its two neighbours value by value with mind-1, mind, mind+1 left out
                             const int thresh = minsad + minsad * a.uniq / 100;
-                            uint32_t umin = sm.ckey[px][CV ? 1 : 0];
+                            uint32_t umin = KEEP ? um_r : sm.ckey[px][CV ? 1 : 0];
                             const int dl = d1 & 7;                     // position of the winner inside its group
 #pragma unroll
                             for (int k = 0; k < 8; k++) { const int dk = 7 - k; umin = (dk < dl - 1 || dk > dl + 1) ? min(umin, vv[k]) : umin; }
@@ -322,10 +353,13 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                         out = valid ? ((d1 * 256 + frac + 15) >> 4) : -16;
                         if (a.cost && valid) a.cost[(size_t)f * a.dframe + (size_t)(yb0 + it - (wsz - 1)) * a.dpitch + ctr0 + px] = (int16_t)minsad;
                     }
-                    if (out_x < a.W) *out_p = (int16_t)out;
+                    *out_p = (int16_t)out;
                 }
             }
             out_p += a.dpitch;
+            // the rows of iteration it+1 were staged before the barrier in the middle of this one (the staging warp overwrites them only after the
+            // next one): their loads are in flight across the back edge instead of at the head of the column-sum step
+            if (WIDE) prefetch_old(b ^ 1);
         }
     } else if (warp == CW) {
         // ======================================================================================

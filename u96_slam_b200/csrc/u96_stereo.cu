@@ -515,7 +515,10 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     } else {
         // chunks of whole BM waves (a chunk that fills half the SMs would make the kernels, not PCIe, the bottleneck)
         const int wave = bm_wave_frames(bm_config(h->bm));
-        int csz = std::max(2 * wave, (32 + wave - 1) / wave * wave);     // two waves per chunk: measured best against the PCIe ceiling
+        // two waves per chunk, one when two would exceed ~128 MB of input (C2 with 148-frame waves: one 296-frame chunk would leave
+        // nothing to overlap inside a step; measured best against the PCIe ceiling: ~148 frames of 640x480)
+        const size_t two_waves_in = (size_t)2 * wave * 2 * W * H;
+        int csz = std::max((two_waves_in <= ((size_t)128 << 20)) ? 2 * wave : wave, (32 + wave - 1) / wave * wave);
         static const int csz_env = getenv("U96_CHUNK") ? atoi(getenv("U96_CHUNK")) : 0;     // developer override (frames per chunk)
         if (csz_env > 0) csz = csz_env;
         if (csz > n) csz = n;

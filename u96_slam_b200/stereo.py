@@ -63,7 +63,7 @@ class RectParams(ctypes.Structure):
 
 
 def lib_path():
-    return os.path.join(PKG, "lib", "libu96stereo.so")
+    return os.environ.get("U96_LIB") or os.path.join(PKG, "lib", "libu96stereo.so")      # U96_LIB: developer A/B builds (tools/ab_build.sh)
 
 
 _LIB = None
