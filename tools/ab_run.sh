@@ -1,1 +1,4 @@
-for v in pf0k0 pf0k1 pf1k0 pf1k1 pf2k0 pf2k1; do echo "== $v"; U96_LIB=u96_slam_b200/lib/ab/$v.so U96_BM_FUSED=1 python tools/bm_time.py 296 all 2>&1 | tail -9 | awk '{print $1,$2,$3,$4,$7,$8,$NF}'; done
+#!/bin/bash
+# Developer tool: times the libraries built by tools/ab_build.sh against the default build on one box.  usage: tools/ab_run.sh [frames] [all]
+echo "== default"; python tools/bm_time.py ${1:-296} $2 2>&1 | tail -9 | awk '{print $1,$2,$3,$4,$7,$8,$NF}'
+for f in u96_slam_b200/lib/ab/*.so; do echo "== $f"; U96_LIB=$f python tools/bm_time.py ${1:-296} $2 2>&1 | tail -9 | awk '{print $1,$2,$3,$4,$7,$8,$NF}'; done
