@@ -427,7 +427,11 @@ int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame
 {
     // the fused-role kernel (bm_fused.cuh) wherever it is the faster one (profiles/r02_summary.md); U96_BM_FUSED = 0 / 1 forces
     // k_bm_fast / k_bm_fused where both apply (developer switch)
-    if (bm_takes_fused(c)) return launch_bm_fused_rtl(xl, xr, pitch, frame, disp, c, n, s);
+    // (a handful of pairs of the saturating 64-disparity chain, which cannot be cut into y-bands, is a latency problem: one CTA per SM,
+    //  ~480 sequential rows; there the V/H-role kernel's row is 15 % shorter -- single pair 0.46 ms against 0.54 ms)
+    static const int fused_env = getenv("U96_BM_FUSED") ? atoi(getenv("U96_BM_FUSED")) : -1;
+    const bool few_sat64 = fused_env != 1 && c.profile == U96_PROFILE_RTL && c.D == 64 && c.wsz * 63 > 1023 && n <= 18;
+    if (bm_takes_fused(c) && !few_sat64) return launch_bm_fused_rtl(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 64) return launch_bm_fast_cs1(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 128) return launch_bm_fast_cs2(xl, xr, pitch, frame, disp, c, n, s);
     return launch_bm_fast_cs4(xl, xr, pitch, frame, disp, c, n, s);

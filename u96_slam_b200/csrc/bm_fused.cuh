@@ -40,18 +40,18 @@ constexpr int U_NC = 160, U_NSEG = 20;                 // tile columns, segments
 #define U96_FUSED_KEEP 1                   // 64 disparities: the winner key and the winner's group stay in registers across the second barrier
 #endif
 #ifndef U96_FUSED_WIDE
-#define U96_FUSED_WIDE 1                   // 0: the saturating RTL variants use the byte rows + PRMT widening of the other variants
+#define U96_FUSED_WIDE 1                   // 0: the RTL variants use the byte rows + PRMT widening of the cv::StereoBM variants
 #endif
 
-// WIDE (the saturating RTL variants): the staged R rows are 16-bit per pixel, so the 8-disparity window of a column is four words
+// WIDE (the RTL variants: 6-bit pixels, column sums below 2048): the staged R rows are 16-bit per pixel, so the 8-disparity window of a column is four words
 // already in the 2 x u16 lane format of the column sums -- aligned words for the odd columns of a segment, and for the even ones
 // seven 16-bit funnel shifts shared by all four of them: no PRMT widening (64 per row and thread) on the ALU pipe, which binds
 // this step, and the oldest row's |l - r| and saturating subtract run on the FMA pipe as fp16 (satsub_absdiff_u16x2).
-template <int NG, bool WIDE>
+template <int NG, bool WIDE, bool SAT>
 struct FusedSmem {
     static constexpr int D = 8 * NG, RLEN = U_NC + D + 16, RB = WIDE ? 2 * RLEN : RLEN, SADP = D + 8, PMS = 9 * NG, NCH = NG / 8;
     // pixels / segments with window sums: a saturating window is at least 17 wide, so a tile holds at most 144 pixels there
-    static constexpr int NPX = WIDE ? 144 : U_NC, NPS = NPX / 8;
+    static constexpr int NPX = (WIDE && SAT) ? 144 : U_NC, NPS = NPX / 8;
     uint4 pre[U_NC + 8][NG];               // inclusive prefix sums inside a segment: [column][group] = 8 x u16; 8 never-written pad columns: the
                                            // unrolled sweep of the last segment reads up to 7 columns past the tile for pixels nobody finishes
     uint16_t sad[NPX][SADP];               // window sums of the row in flight; pitch 2D+16 B: rows skew over the banks
@@ -63,7 +63,7 @@ struct FusedSmem {
                                            // OPENCV = u32 [1 + column] prefix sums over the columns of the texture column sums (entry 0 = 0)
     uint8_t rrow[2][2][RB];                // [buffer][newest / oldest] R row segment: R[xs - D - 8 .. xs + 168); WIDE: u16 per pixel
     uint32_t lrow4[2][2][U_NC];            // L row segment, every pixel replicated into the four bytes of a word (VABSDIFF4 operand); WIDE: into its two halves
-    uint8_t lrow[2][2][U_NC];              // L row segment (guard warp: 8 columns per word pair)
+    uint8_t lrow[2][2][WIDE ? 4 : U_NC];   // L row segment as bytes (guard warp of the byte-row variants: 8 columns per word pair)
 };
 
 // |l - r| on two u16 lanes below 2048 and max(c - |l - r|, 0), both on the FMA pipe (see satsub_u16x2): HADD2 + HADD2.SAT with -|.| folded
@@ -94,11 +94,11 @@ template <int PROFILE, bool SAT, int NG>
 __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fused(const FastArgs a)
 {
     constexpr bool CV = (PROFILE == U96_PROFILE_OPENCV);
-    constexpr bool WIDE = U96_FUSED_WIDE && !CV && SAT;
+    constexpr bool WIDE = U96_FUSED_WIDE && !CV;
     constexpr bool KEEP = U96_FUSED_KEEP && NG == 8;
     // same-box A/B (profiles/r02_summary.md): the 72-register variants without the wide rows lose 4 % to a two-pixel look-ahead
     constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? (WIDE ? 2 : 0) : (NG == 16) ? 2 : 1;
-    using SM = FusedSmem<NG, WIDE>;
+    using SM = FusedSmem<NG, WIDE, SAT>;
     constexpr int D = SM::D, RLEN = SM::RLEN, RB = SM::RB, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
     constexpr int LG = (NG == 8) ? 3 : (NG == 16) ? 4 : 5;
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             uint4 run;                                                // prefix sums of the 8 columns; after phase 1: the block sum
             // ---- phase 1: the newest and the oldest row enter the 64 column sums of this thread ----
             if constexpr (WIDE) {
-                // oldest row first, on the FMA pipe: c = max(c - |l - r|, 0); then the newest row on the ALU pipe: c = min(c + |l - r|, 1023)
+                // oldest row first, on the FMA pipe: c = max(c - |l - r|, 0); then the newest row: c = min(c + |l - r|, 1023) on the ALU pipe
+                // (exact sums, window <= 16: the same without the ceiling -- the subtraction never clamps and the add is a plain one)
                 uint4 *prow = &sm.pre[8 * s][g];
                 {
                     const uint4 e0 = pf_e0, e1 = pf_e1, la = pf_la, lb = pf_lb;
@@ -182,8 +183,12 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const uint32_t *w = (i & 1) ? &ew[(i + 1) >> 1] : &ow[i >> 1];
-                        c[i].x = __viaddmin_u16x2(c[i].x, __vabsdiffu4(lw[i], w[0]), 0x03FF03FFu); c[i].y = __viaddmin_u16x2(c[i].y, __vabsdiffu4(lw[i], w[1]), 0x03FF03FFu);
-                        c[i].z = __viaddmin_u16x2(c[i].z, __vabsdiffu4(lw[i], w[2]), 0x03FF03FFu); c[i].w = __viaddmin_u16x2(c[i].w, __vabsdiffu4(lw[i], w[3]), 0x03FF03FFu);
+                        if (SAT) {
+                            c[i].x = __viaddmin_u16x2(c[i].x, __vabsdiffu4(lw[i], w[0]), 0x03FF03FFu); c[i].y = __viaddmin_u16x2(c[i].y, __vabsdiffu4(lw[i], w[1]), 0x03FF03FFu);
+                            c[i].z = __viaddmin_u16x2(c[i].z, __vabsdiffu4(lw[i], w[2]), 0x03FF03FFu); c[i].w = __viaddmin_u16x2(c[i].w, __vabsdiffu4(lw[i], w[3]), 0x03FF03FFu);
+                        } else {
+                            c[i].x += __vabsdiffu4(lw[i], w[0]); c[i].y += __vabsdiffu4(lw[i], w[1]); c[i].z += __vabsdiffu4(lw[i], w[2]); c[i].w += __vabsdiffu4(lw[i], w[3]);
+                        }
                         run.x += c[i].x; run.y += c[i].y; run.z += c[i].z; run.w += c[i].w;
                         prow[NG * i] = run;
                     }
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             m[j] = (x0 & 3) * 8;
             ok0[j] = on[j] && w0 >= 0 && w0 < pw; ok1[j] = on[j] && w0 + 1 >= 0 && w0 + 1 < pw;
             p[j] = reinterpret_cast<const uint32_t *>(isr ? gr : gl) + ((ptrdiff_t)(yb0 - h - (rt[j] ? wsz : 0)) * pw + w0);
-            so[j] = (uint32_t)((isr ? offsetof(SM, rrow) + (size_t)rt[j] * RB + (WIDE ? 8 : 4) * q : offsetof(SM, lrow) + (size_t)rt[j] * U_NC + 4 * q));
+            so[j] = (uint32_t)((isr ? offsetof(SM, rrow) + (size_t)rt[j] * RB + (WIDE ? 8 : 4) * q : offsetof(SM, lrow4) + (size_t)rt[j] * 4 * U_NC + 16 * q));
 
         }
         uint32_t w0r[NI], w1r[NI];
@@ -401,16 +406,17 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                 if (on[j]) {
                     const bool isr = (lane + 32 * j) < 2 * RW;
                     const uint32_t v = __funnelshift_r(w0r[j], w1r[j], m[j]) & (CV ? 0xFFFFFFFFu : 0x3F3F3F3Fu);
-                    unsigned char *dst = usm_raw + so[j] + boff * (isr ? RB : U_NC);
-                    if (WIDE && isr) {
-                        *reinterpret_cast<uint2 *>(dst) = make_uint2(fprmt(v, 0, 0x4140), fprmt(v, 0, 0x4342));       // pixels 4q .. 4q+3 as u16
-                    } else {
-                        *reinterpret_cast<uint32_t *>(dst) = v;
-                    }
-                    if (!isr) {                                       // L pixels once more, replicated for the compute threads
+                    unsigned char *dst = usm_raw + so[j] + boff * (isr ? RB : 4 * U_NC);
+                    if (isr) {
+                        if (WIDE) *reinterpret_cast<uint2 *>(dst) = make_uint2(fprmt(v, 0, 0x4140), fprmt(v, 0, 0x4342));      // pixels 4q .. 4q+3 as u16
+                        else *reinterpret_cast<uint32_t *>(dst) = v;
+                    } else {                                          // L pixels replicated for the compute threads (+ as bytes for the guard warp)
                         constexpr uint32_t REP = WIDE ? 0x00010001u : 0x01010101u;
-                        const uint32_t o4 = (uint32_t)offsetof(SM, lrow4) + 4u * (so[j] - (uint32_t)offsetof(SM, lrow)) + boff * 4u * U_NC;
-                        *reinterpret_cast<uint4 *>(usm_raw + o4) = make_uint4((v & 0xFFu) * REP, ((v >> 8) & 0xFFu) * REP, ((v >> 16) & 0xFFu) * REP, (v >> 24) * REP);
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4((v & 0xFFu) * REP, ((v >> 8) & 0xFFu) * REP, ((v >> 16) & 0xFFu) * REP, (v >> 24) * REP);
+                        if (!WIDE) {
+                            const uint32_t o1 = (uint32_t)offsetof(SM, lrow) + (so[j] - (uint32_t)offsetof(SM, lrow4)) / 4u + boff * U_NC;
+                            *reinterpret_cast<uint32_t *>(usm_raw + o1) = v;
+                        }
                     }
                 }
         };
@@ -467,8 +473,8 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                         uint16_t *gd = reinterpret_cast<uint16_t *>(&sm.gt[b][0]) + which * (U_NC + 8);
                         if constexpr (WIDE) {
                             // R(x - D): halves 8s+8 ..; R(x + 1): halves 8s+D+9 .. (one pixel past an aligned quad); L pairs widened here
-                            const uint2 ln = *reinterpret_cast<const uint2 *>(&sm.lrow[b][0][8 * s]);
-                            const uint2 lo = *reinterpret_cast<const uint2 *>(&sm.lrow[b][1][8 * s]);
+                            const uint4 *lnp = reinterpret_cast<const uint4 *>(&sm.lrow4[b][0][8 * s]), *lop = reinterpret_cast<const uint4 *>(&sm.lrow4[b][1][8 * s]);
+                            const uint4 lna = lnp[0], lnb = lnp[1], loa = lop[0], lob = lop[1];       // one word (l, 0, l, 0) per column
                             const int ro = which ? 2 * (8 * s + 8) : 2 * (8 * s + D + 8);
                             uint4 rn = *reinterpret_cast<const uint4 *>(&sm.rrow[b][0][ro]), rold = *reinterpret_cast<const uint4 *>(&sm.rrow[b][1][ro]);
                             if (!which) {
@@ -476,12 +482,15 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                                 rn = make_uint4(__funnelshift_r(rn.x, rn.y, 16), __funnelshift_r(rn.y, rn.z, 16), __funnelshift_r(rn.z, rn.w, 16), __funnelshift_r(rn.w, tn, 16));
                                 rold = make_uint4(__funnelshift_r(rold.x, rold.y, 16), __funnelshift_r(rold.y, rold.z, 16), __funnelshift_r(rold.z, rold.w, 16), __funnelshift_r(rold.w, to, 16));
                             }
-                            cc.x = satsub_absdiff_u16x2(cc.x, fprmt(lo.x, 0, 0x4140), rold.x); cc.y = satsub_absdiff_u16x2(cc.y, fprmt(lo.x, 0, 0x4342), rold.y);
-                            cc.z = satsub_absdiff_u16x2(cc.z, fprmt(lo.y, 0, 0x4140), rold.z); cc.w = satsub_absdiff_u16x2(cc.w, fprmt(lo.y, 0, 0x4342), rold.w);
-                            cc.x = __viaddmin_u16x2(cc.x, __vabsdiffu4(fprmt(ln.x, 0, 0x4140), rn.x), 0x03FF03FFu);
-                            cc.y = __viaddmin_u16x2(cc.y, __vabsdiffu4(fprmt(ln.x, 0, 0x4342), rn.y), 0x03FF03FFu);
-                            cc.z = __viaddmin_u16x2(cc.z, __vabsdiffu4(fprmt(ln.y, 0, 0x4140), rn.z), 0x03FF03FFu);
-                            cc.w = __viaddmin_u16x2(cc.w, __vabsdiffu4(fprmt(ln.y, 0, 0x4342), rn.w), 0x03FF03FFu);
+                            // columns (i, i+1) of the pair: low half of word i, high half of word i+1
+                            cc.x = satsub_absdiff_u16x2(cc.x, fprmt(loa.x, loa.y, 0x7610), rold.x); cc.y = satsub_absdiff_u16x2(cc.y, fprmt(loa.z, loa.w, 0x7610), rold.y);
+                            cc.z = satsub_absdiff_u16x2(cc.z, fprmt(lob.x, lob.y, 0x7610), rold.z); cc.w = satsub_absdiff_u16x2(cc.w, fprmt(lob.z, lob.w, 0x7610), rold.w);
+                            const uint32_t n0 = __vabsdiffu4(fprmt(lna.x, lna.y, 0x7610), rn.x), n1 = __vabsdiffu4(fprmt(lna.z, lna.w, 0x7610), rn.y);
+                            const uint32_t n2 = __vabsdiffu4(fprmt(lnb.x, lnb.y, 0x7610), rn.z), n3 = __vabsdiffu4(fprmt(lnb.z, lnb.w, 0x7610), rn.w);
+                            if (SAT) {
+                                cc.x = __viaddmin_u16x2(cc.x, n0, 0x03FF03FFu); cc.y = __viaddmin_u16x2(cc.y, n1, 0x03FF03FFu);
+                                cc.z = __viaddmin_u16x2(cc.z, n2, 0x03FF03FFu); cc.w = __viaddmin_u16x2(cc.w, n3, 0x03FF03FFu);
+                            } else { cc.x += n0; cc.y += n1; cc.z += n2; cc.w += n3; }
                             *reinterpret_cast<uint4 *>(gd + 8 * s) = cc;
                         } else {
                         uint2 rv[2];
@@ -520,7 +529,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
 template <int PROFILE, bool SAT, int NG>
 static inline void fused_go(const FastArgs &a, int n, cudaStream_t s)
 {
-    const int smem = (int)sizeof(FusedSmem<NG, U96_FUSED_WIDE && PROFILE == U96_PROFILE_RTL && SAT>);
+    const int smem = (int)sizeof(FusedSmem<NG, U96_FUSED_WIDE && PROFILE == U96_PROFILE_RTL, SAT>);
     cudaFuncSetAttribute(k_bm_fused<PROFILE, SAT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k_bm_fused<PROFILE, SAT, NG><<<dim3(a.ntx_tiles, a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
 }
