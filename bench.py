@@ -709,12 +709,12 @@ def main():
         traffic, traffic_note = None, "no capture for this build"
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "bm_traffic.json")))
-            lib_sha = hashlib.sha256(open(u.lib_path(), "rb").read()).hexdigest()[:16]
-            if tr.get("workload") == args.workload and tr.get("lib_sha16") == lib_sha:
+            from u96_slam_b200 import build as _build
+            if tr.get("workload") == args.workload and tr.get("src_sha16") == _build.source_sha16():
                 traffic = tr.get("dram_bytes_per_frame") * nb
-                traffic_note = f"ncu --set full capture of this very library build ({tr.get('source')})"
+                traffic_note = f"ncu --set full capture of these very kernel sources ({tr.get('source')})"
             elif tr.get("workload") == args.workload:
-                traffic_note = f"profiles/bm_traffic.json was captured with another build (lib {tr.get('lib_sha16')}): not reported"
+                traffic_note = f"profiles/bm_traffic.json was captured with other kernel sources ({tr.get('src_sha16')}): not reported"
         except (OSError, TypeError):
             pass
         bm_ms = stage["bm"]
@@ -723,8 +723,9 @@ def main():
                     "peak_source": "measured live: u96_microbench VABSDIFF4 issue rate (ALU pipe, 64 lanes/clk/SM); "
                                    "MEASURED_PEAKS.json has no integer figure",
                     "algorithmic_ops_per_launch": bmr["algorithmic_ops_per_launch"], "kernel_ms": bm_ms, "traffic": traffic, "traffic_note": traffic_note,
-                    "binding_resource": "shared-memory data pipe: ncu l1tex__data_pipe_lsu_wavefronts_mem_shared 77-80 % of peak, ALU pipe 62-64 %, "
-                                        "issue slots 63 % (profiles/r02_summary.md)",
+                    "binding_resource": "no unit saturated (ncu: issue slots 65 %, ALU pipe 54 %, FMA pipe 25 %, shared-memory data pipe 65 % of peak): "
+                                        "two CTA barriers per image row and dependent shared-memory loads leave 5 compute warps per scheduler "
+                                        "latency bound (profiles/r02_summary.md)",
                     "hbm": {"achieved": 4.0 * W * H * nb / (bm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": 4.0 * W * H * nb / (bm_ms * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

@@ -8,11 +8,11 @@ python bench.py > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_ref.json 2>> $O/${TAG}_bench_n1.err
 python tools/bm_time.py 296 all > $O/${TAG}_bm_time.log 2>&1
 U96_BM_FUSED=0 python tools/bm_time.py 296 all > $O/${TAG}_bm_time_fast.log 2>&1
-U96_BM_FUSED=1 python tools/bm_time.py 296 > $O/${TAG}_bm_time_fused64.log 2>&1
 python tools/stage_time.py > $O/${TAG}_stage_time.log 2>&1
 python tools/post_time.py 296 > $O/${TAG}_post_time.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 4 --warmup 3 --reps 1 --no-cpu-baseline > /dev/null 2>&1
-$NCU -k regex:k_bm_fast -s 2 -c 1 -o $O/${TAG}_bm64   python tools/bm_one.py 640 480 64 21 0 296 4 > /dev/null 2>&1
+$NCU -k regex:k_bm_fused -s 2 -c 1 -o $O/${TAG}_bm64   python tools/bm_one.py 640 480 64 21 0 296 4 > /dev/null 2>&1
+U96_BM_FUSED=0 $NCU -k regex:k_bm_fast -s 2 -c 1 -o $O/${TAG}_bm64fast python tools/bm_one.py 640 480 64 21 0 296 4 > /dev/null 2>&1
 $NCU -k regex:k_bm_fused -s 2 -c 1 -o $O/${TAG}_bm64b15 python tools/bm_one.py 640 480 64 15 0 296 4 > /dev/null 2>&1
 $NCU -k regex:k_bm_fused -s 2 -c 1 -o $O/${TAG}_bmcv64 python tools/bm_one.py 640 480 64 21 1 296 4 > /dev/null 2>&1
 $NCU -k regex:k_bm_fused -s 2 -c 1 -o $O/${TAG}_bm128  python tools/bm_one.py 1242 375 128 15 0 148 4 > /dev/null 2>&1

@@ -1,7 +1,7 @@
 """Write profiles/bm_traffic.json from an `ncu --set full` capture of the BM kernel (developer tool).
 usage: make_traffic.py report.ncu-rep workload frames_per_launch
-The file records the SHA-256 of the library the capture was taken with; bench.py reports `roofline.traffic` only when that
-equals the library it is running (a capture of another build is stale by construction)."""
+The file records a SHA-256 over the CUDA sources the capture was taken with; bench.py reports `roofline.traffic` only when that
+equals the sources of the library it is running (a capture of other code is stale by construction)."""
 import csv
 import hashlib
 import json
@@ -23,10 +23,11 @@ def val(name):
 
 
 rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
-lib = os.path.join(ROOT, "u96_slam_b200", "lib", "libu96stereo.so")
+sys.path.insert(0, ROOT)
+from u96_slam_b200 import build as _build  # noqa: E402
 d = {"workload": workload, "kernel": v[h.index("Kernel Name")], "frames_per_launch": frames, "dram_bytes_read": int(rd),
      "dram_bytes_write": int(wr), "dram_bytes_per_frame": int((rd + wr) / frames),
-     "lib_sha16": hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16],
+     "src_sha16": _build.source_sha16(),
      "source": f"{os.path.basename(rep)}: ncu --set full --clock-control none, {frames} frames per launch"}
 json.dump(d, open(os.path.join(ROOT, "profiles", "bm_traffic.json"), "w"), indent=1)
 print(d)
