@@ -13,7 +13,7 @@ sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active
 sm__warps_active.avg.pct_of_peak_sustained_active
 l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
 l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum
-l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed
+l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed
 dram__bytes_read.sum
 dram__bytes_write.sum
 launch__registers_per_thread
