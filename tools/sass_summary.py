@@ -1,6 +1,6 @@
 """Opcode histogram per kernel of libu96stereo.so (developer tool): `cuobjdump -sass` -> profiles/sass_summary.txt.
 Shows which machine instructions the claims in DESIGN.md rest on (UTMALDG = TMA tensor load, SYNCS = mbarrier,
-STAS = st.async to a peer CTA's shared memory, VABSDIFF4 / VIADDMNMX / VIMNMX = packed integer SIMD, IDP = dp2a/dp4a, REDUX)."""
+STAS = st.async to a peer CTA's shared memory, VABSDIFF4 / VIADDMNMX / VIMNMX = packed integer SIMD, IDP = dp2a/dp4a, HADD2 / HFMA2 = the fp16 forms of the saturating subtract and the abs-diff of the fused BM kernel, REDUX)."""
 import collections
 import hashlib
 import os
@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "u96_slam_b200", "lib", "libu96stereo.so")
-KEY = ["UTMALDG", "SYNCS", "STAS", "VABSDIFF4", "VIADDMNMX", "VIMNMX3", "VIMNMX", "IDP", "PRMT", "SHF", "REDUX", "LDS", "STS", "LDG", "STG",
+KEY = ["UTMALDG", "SYNCS", "STAS", "VABSDIFF4", "VIADDMNMX", "VIMNMX3", "VIMNMX", "HADD2", "HFMA2", "IDP", "PRMT", "SHF", "REDUX", "LDS", "STS", "LDG", "STG",
        "ATOMS", "ATOMG", "RED", "BAR", "SHFL", "MUFU", "FFMA", "IMAD", "DFMA", "DMUL", "DADD", "HMMA", "UTCHMMA", "MEMBAR"]
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
