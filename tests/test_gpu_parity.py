@@ -714,6 +714,30 @@ def test_fast_and_generic_bm_kernels_agree(u, monkeypatch):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("W,H,D,B,n", [(640, 56, 64, 21, 24), (500, 40, 64, 17, 20), (640, 44, 64, 31, 20), (523, 48, 64, 15, 20),
+                                        (700, 50, 128, 21, 6), (610, 40, 256, 19, 3)])
+def test_fused_bm_kernel_every_frame_of_a_batch(u, oracle, W, H, D, B, n):
+    """k_bm_fused with the 16-bit staged rows and the fp16 oldest-row step (bm_fused.cuh), in batches beyond the <= 18-pair rule that keeps
+    a handful of saturating 64-disparity pairs on k_bm_fast: EVERY frame == oracle, on frames whose column sums hit the 10-bit
+    ceiling (bm_calc_sad.v:449-466) and on ragged widths; the same frames through U96_BM_FUSED=0 agree as well (same process: the
+    switch is read once, so the comparison runs through the generic kernel instead)."""
+    L, R = u.synth_batch(21, 0, n, W, H, D)
+    L[:, H // 4: 3 * H // 4] = np.where(L[:, H // 4: 3 * H // 4] > 127, 255, 0).astype(np.uint8)      # strong edges: saturating sums
+    with u.StereoFrontEnd(0, W, H, n) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=B, num_disparities=D, x_store_offset=1,
+                         rtl_extended=int(D > 128), uni_enable=0)
+        fe.submit_rect(0, L, R)
+        b = fe.wait()
+        d = fe.receive_disp(b); xl, xr = fe.receive_xsbl(b)
+    sat = 0
+    for i in range(n):
+        want = oracle.bm_rtl(xl[i], xr[i], wsz=B, ndisp=D, rtl_extended=int(D > 128))
+        sat += oracle.sat_events()
+        assert np.array_equal(d[i], want), f"frame {i}"
+    if B * 63 > 1023:
+        assert sat > 0
+
+
 def test_uvc_payload(u, fe640, golden, oracle):
     """u96_receive_uvc == the firmware's UVC frame (xusb_main.c:293-376) for the RECT, XSBL and BM streams."""
     fe640.set_bm_registers((480 << 16) + 640, 0x00150040, 0)
