@@ -47,7 +47,7 @@ constexpr int U_NC = 160, U_NSEG = 20;                 // tile columns, segments
 // already in the 2 x u16 lane format of the column sums -- aligned words for the odd columns of a segment, and for the even ones
 // seven 16-bit funnel shifts shared by all four of them: no PRMT widening (64 per row and thread) on the ALU pipe, which binds
 // this step, and the oldest row's |l - r| and saturating subtract run on the FMA pipe as fp16 (satsub_absdiff_u16x2).
-template <int NG, bool WIDE, bool SAT>
+template <int NG, bool WIDE, bool SAT, bool CV>
 struct FusedSmem {
     static constexpr int D = 8 * NG, RLEN = U_NC + D + 16, RB = WIDE ? 2 * RLEN : RLEN, SADP = D + 8, PMS = 9 * NG, NCH = NG / 8;
     // pixels / segments with window sums: a saturating window is at least 17 wide, so a tile holds at most 144 pixels there
@@ -57,13 +57,14 @@ struct FusedSmem {
     uint16_t sad[NPX][SADP];               // window sums of the row in flight; pitch 2D+16 B: rows skew over the banks
     uint32_t pmin[NPS][PMS];            // packed minima [segment][pixel j][group] (odd | even disparities); 9*NG-word segment stride: the
                                            // segments of a warp store to disjoint banks
-    uint32_t ckey[NPX][WIDE ? 1 : 2];     // per pixel: winner key (min SAD << 8 | group code) and, OPENCV, the smallest group minimum outside the
+    static constexpr bool KEEP = U96_FUSED_KEEP && NG == 8;      // winner key and group stay in registers: ckey is not used
+    uint32_t ckey[KEEP ? 4 : NPX][CV ? 2 : 1];     // per pixel: winner key (min SAD << 8 | group code) and, OPENCV, the smallest group minimum outside the
                                            // winner's group and its two neighbours
     uint32_t gt[2][U_NC + 8];              // output of the guard warp, [buffer]: RTL = u16 [d=-1 / d=D][column] column sums of the guard lanes;
                                            // OPENCV = u32 [1 + column] prefix sums over the columns of the texture column sums (entry 0 = 0)
     uint8_t rrow[2][2][RB];                // [buffer][newest / oldest] R row segment: R[xs - D - 8 .. xs + 168); WIDE: u16 per pixel
     uint32_t lrow4[2][2][U_NC];            // L row segment, every pixel replicated into the four bytes of a word (VABSDIFF4 operand); WIDE: into its two halves
-    uint8_t lrow[2][2][WIDE ? 4 : U_NC];   // L row segment as bytes (guard warp of the byte-row variants: 8 columns per word pair)
+    uint8_t lrow[2][2][(WIDE && !CV) ? 4 : U_NC];   // L row segment as bytes (guard warp: byte-row variants, and the OPENCV texture sums)
 };
 
 // |l - r| on two u16 lanes below 2048 and max(c - |l - r|, 0), both on the FMA pipe (see satsub_u16x2): HADD2 + HADD2.SAT with -|.| folded
@@ -90,15 +91,15 @@ __device__ __forceinline__ uint2 r_window(uint2 a, uint2 b, int i)
 // resident CTAs per SM: 64 disparities 4 (54.5 KB, 72 registers), 128: 2, 256: 1
 __host__ __device__ constexpr int fused_occupancy(int ng) { return ng == 8 ? 4 : ng == 16 ? 2 : 1; }
 
-template <int PROFILE, bool SAT, int NG>
+template <int PROFILE, bool SAT, int NG, bool WD>
 __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fused(const FastArgs a)
 {
     constexpr bool CV = (PROFILE == U96_PROFILE_OPENCV);
-    constexpr bool WIDE = U96_FUSED_WIDE && !CV;
-    constexpr bool KEEP = U96_FUSED_KEEP && NG == 8;
+    constexpr bool WIDE = U96_FUSED_WIDE && WD;                  // RTL: always; OPENCV: when window x 2 cap < 2048 (column sums exact as fp16)
+    constexpr bool KEEP = FusedSmem<NG, WIDE, SAT, CV>::KEEP;
     // same-box A/B (profiles/r02_summary.md): the 72-register variants without the wide rows lose 4 % to a two-pixel look-ahead
     constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? (WIDE ? 2 : 0) : (NG == 16) ? 2 : 1;
-    using SM = FusedSmem<NG, WIDE, SAT>;
+    using SM = FusedSmem<NG, WIDE, SAT, CV>;
     constexpr int D = SM::D, RLEN = SM::RLEN, RB = SM::RB, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
     constexpr int LG = (NG == 8) ? 3 : (NG == 16) ? 4 : 5;
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                     } else {                                          // L pixels replicated for the compute threads (+ as bytes for the guard warp)
                         constexpr uint32_t REP = WIDE ? 0x00010001u : 0x01010101u;
                         *reinterpret_cast<uint4 *>(dst) = make_uint4((v & 0xFFu) * REP, ((v >> 8) & 0xFFu) * REP, ((v >> 16) & 0xFFu) * REP, (v >> 24) * REP);
-                        if (!WIDE) {
+                        if (!WIDE || CV) {
                             const uint32_t o1 = (uint32_t)offsetof(SM, lrow) + (so[j] - (uint32_t)offsetof(SM, lrow4)) / 4u + boff * U_NC;
                             *reinterpret_cast<uint32_t *>(usm_raw + o1) = v;
                         }
@@ -526,12 +527,12 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
     }
 }
 
-template <int PROFILE, bool SAT, int NG>
+template <int PROFILE, bool SAT, int NG, bool WD>
 static inline void fused_go(const FastArgs &a, int n, cudaStream_t s)
 {
-    const int smem = (int)sizeof(FusedSmem<NG, U96_FUSED_WIDE && PROFILE == U96_PROFILE_RTL, SAT>);
-    cudaFuncSetAttribute(k_bm_fused<PROFILE, SAT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_bm_fused<PROFILE, SAT, NG><<<dim3(a.ntx_tiles, a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
+    const int smem = (int)sizeof(FusedSmem<NG, U96_FUSED_WIDE && WD, SAT, PROFILE == U96_PROFILE_OPENCV>);
+    cudaFuncSetAttribute(k_bm_fused<PROFILE, SAT, NG, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_bm_fused<PROFILE, SAT, NG, WD><<<dim3(a.ntx_tiles, a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
 }
 
 // 64 / 128 / 256 disparities, window 9..31; RTL profile with the uniqueness filter off, or the cv::StereoBM profile
@@ -552,14 +553,20 @@ static inline int launch_bm_fused(const uint8_t *xl, const uint8_t *xr, int pitc
     if (a.ctr_hi < a.ctr_lo || a.y_hi < a.y_lo) return 0;
     constexpr int R = U96_PROFILE_RTL, V = U96_PROFILE_OPENCV;
     if (c.profile == U96_PROFILE_OPENCV) {
-        if (ng == 8) fused_go<V, false, 8>(a, n, s); else if (ng == 16) fused_go<V, false, 16>(a, n, s); else fused_go<V, false, 32>(a, n, s);
+        // 16-bit rows + fp16 oldest-row step when every column sum is exact as fp16: window x max |difference| (= 2 cap, xsobel clip) < 2048
+        // (the reference's own configuration, main.cpp:198-212: cap 31, window 21)
+        static const int cvw_env = getenv("U96_CV_WIDE") ? atoi(getenv("U96_CV_WIDE")) : 1;      // developer switch
+        const bool wide = cvw_env && (c.wsz * 2 * c.cap < 2048);
+        if (ng == 8)       fused_go<V, false, 8, false>(a, n, s);   // (measured: at 72 registers the wide form spills and is 1 % slower here; +2.5 % / +11 % at 128 / 256)
+        else if (ng == 16) { if (wide) fused_go<V, false, 16, true>(a, n, s); else fused_go<V, false, 16, false>(a, n, s); }
+        else               { if (wide) fused_go<V, false, 32, true>(a, n, s); else fused_go<V, false, 32, false>(a, n, s); }
         return 1;
     }
     const bool sat = c.wsz * 63 > 1023;
     if (sat && a.TX > 144) return 0;                                             // cannot happen (window >= 17): FusedSmem::NPX
-    if (ng == 8)       { if (sat) fused_go<R, true, 8>(a, n, s);  else fused_go<R, false, 8>(a, n, s); }
-    else if (ng == 16) { if (sat) fused_go<R, true, 16>(a, n, s); else fused_go<R, false, 16>(a, n, s); }
-    else               { if (sat) fused_go<R, true, 32>(a, n, s); else fused_go<R, false, 32>(a, n, s); }
+    if (ng == 8)       { if (sat) fused_go<R, true, 8, true>(a, n, s);  else fused_go<R, false, 8, true>(a, n, s); }
+    else if (ng == 16) { if (sat) fused_go<R, true, 16, true>(a, n, s); else fused_go<R, false, 16, true>(a, n, s); }
+    else               { if (sat) fused_go<R, true, 32, true>(a, n, s); else fused_go<R, false, 32, true>(a, n, s); }
     return 1;
 }
 
