@@ -379,15 +379,19 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_rect_remap_tma(const __grid_c
         const uint32_t w0 = smem_u32(rt_smem) + (uint32_t)(o0[0] & ~3), w1 = smem_u32(rt_smem) + (uint32_t)(o0[1] & ~3);
         const uint32_t rowb = (uint32_t)BW;
         auto lds = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
-        auto group = [&](uint32_t a, uint32_t mi, const uint32_t (&sel)[4], const uint32_t (&wg)[4][3], bool three_rows) {
+        // one PRMT gathers the tap pairs of TWO pixels (bytes x0, x0+1, x1, x1+1): dp2a.lo takes the first pair, dp2a.hi the second
+        const uint32_t sel2[2][2] = {{selw[0][0] | (selw[0][1] << 8), selw[0][2] | (selw[0][3] << 8)},
+                                     {selw[1][0] | (selw[1][1] << 8), selw[1][2] | (selw[1][3] << 8)}};
+        auto group = [&](uint32_t a, uint32_t mi, const uint32_t (&sel)[2], const uint32_t (&wg)[4][3], bool three_rows) {
             uint32_t acc[4] = {1u << 15, 1u << 15, 1u << 15, 1u << 15};
 #pragma unroll
             for (int r = 0; r < 3; r++) {
                 if (r == 2 && !three_rows) break;
                 const uint32_t a0 = lds(a + r * rowb), a1 = lds(a + r * rowb + 4), a2 = lds(a + r * rowb + 8);
                 const uint32_t lo = __funnelshift_r(a0, a1, mi), hi = __funnelshift_r(a1, a2, mi);
-#pragma unroll
-                for (int k = 0; k < 4; k++) acc[k] = __dp2a_lo(wg[k][r], __byte_perm(lo, hi, sel[k]), acc[k]);
+                const uint32_t p01 = __byte_perm(lo, hi, sel[0]), p23 = __byte_perm(lo, hi, sel[1]);
+                acc[0] = __dp2a_lo(wg[0][r], p01, acc[0]); acc[1] = __dp2a_hi(wg[1][r], p01, acc[1]);
+                acc[2] = __dp2a_lo(wg[2][r], p23, acc[2]); acc[3] = __dp2a_hi(wg[3][r], p23, acc[3]);
             }
             const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
             return __byte_perm(p01, p23, 0x5410);
@@ -406,8 +410,8 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_rect_remap_tma(const __grid_c
                     mbar_wait(&full[s], ph);
                     const uint32_t soff = (uint32_t)s * (uint32_t)stage_bytes;
                     uint32_t out0, out1;
-                    if (r3) { out0 = group(w0 + soff, mis[0], selw[0], wr[0], true);  out1 = group(w1 + soff, mis[1], selw[1], wr[1], true); }
-                    else    { out0 = group(w0 + soff, mis[0], selw[0], wr[0], false); out1 = group(w1 + soff, mis[1], selw[1], wr[1], false); }
+                    if (r3) { out0 = group(w0 + soff, mis[0], sel2[0], wr[0], true);  out1 = group(w1 + soff, mis[1], sel2[1], wr[1], true); }
+                    else    { out0 = group(w0 + soff, mis[0], sel2[0], wr[0], false); out1 = group(w1 + soff, mis[1], sel2[1], wr[1], false); }
                     __syncwarp();
                     if (leader) mbar_arrive(&empty[s]);
                     asm volatile("st.global.u32 [%0], %1;" ::"l"(d0), "r"(out0) : "memory");      // (the laundered pointers are generic to the compiler)
