@@ -131,7 +131,7 @@ static int validate_bm(const u96_handle *h, const u96_bm_params &p)
         if (p.uniqueness_ratio < 0 || p.texture_threshold < 0) return U96_ERR_INVALID;
         if (p.speckle_window_size < 0 || p.speckle_window_size > 1000000) return U96_ERR_INVALID;
         if (p.width - p.num_disparities + 1 - 2 * hw <= 0) return U96_ERR_INVALID;
-        if (p.disp12_max_diff >= 0 && (size_t)p.width * 8 > 227 * 1024) return U96_ERR_UNSUPPORTED;   // k_validate keeps one row of keys in shared memory
+        if (p.disp12_max_diff >= 0 && (size_t)p.width * 4 > 227 * 1024) return U96_ERR_UNSUPPORTED;   // k_validate keeps one row of 32-bit keys in shared memory
         max_ad = 2 * p.prefilter_cap;
     } else return U96_ERR_INVALID;
     if (p.height - 2 * hw <= 0) return U96_ERR_INVALID;
