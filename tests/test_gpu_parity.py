@@ -628,6 +628,23 @@ def test_opencv_postfilters(u, fe640, golden, cv_golden, oracle):
     fe640.set_bm_params(disp12_max_diff=-1, speckle_window_size=0, speckle_range=0)
 
 
+@pytest.mark.parametrize("W,H", [(332, 70), (330, 64), (648, 50), (2056, 40)])
+def test_opencv_postfilters_ragged_widths(u, oracle, W, H):
+    """validateDisparity + filterSpeckles on widths that take the other code paths of postfilter.cu: a multiple of 4 but not of 8 (scalar
+    row pass, four-pixel passes), not a multiple of 4 (scalar everywhere), a multiple of 8 (vector row pass), wider than 2048."""
+    D, n = 64, 2
+    L, R = u.synth_batch(13, 2, n, W, H, D)
+    with u.StereoFrontEnd(0, W, H, n) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_OPENCV, num_disparities=D, block_size=11, texture_threshold=5,
+                         uniqueness_ratio=5, prefilter_cap=31, min_disparity=0, disp12_max_diff=1, speckle_window_size=40, speckle_range=24)
+        fe.submit_rect(0, L, R)
+        got = fe.receive_disp(fe.wait())
+    for i in range(n):
+        want = oracle.bm_cv_post(oracle.xsobel_cv(L[i]), oracle.xsobel_cv(R[i]), wsz=11, ndisp=D, texture_threshold=5, uniqueness_ratio=5,
+                                 disp12_max_diff=1, speckle_window=40, speckle_range=24)
+        assert np.array_equal(got[i], want), (i, int((got[i] != want).sum()))
+
+
 def test_stereobm_facade_maincpp_configuration(u, golden, cv_golden):
     bm = u.StereoBM.create(16, 9)                                         # main.cpp:201
     bm.setPreFilterCap(31); bm.setBlockSize(21); bm.setMinDisparity(0); bm.setNumDisparities(64)

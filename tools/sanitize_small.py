@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import u96_slam_b200 as u  # noqa: E402
 
 CONFIGS = ((640, 96, 64, 21, 0, 0), (640, 96, 64, 15, 0, 0), (640, 96, 64, 21, 0, 1), (640, 96, 64, 15, 1, 0), (330, 80, 128, 9, 0, 0),
-                                (330, 80, 128, 9, 1, 0), (530, 70, 256, 21, 0, 0), (530, 70, 256, 11, 1, 0), (200, 64, 96, 7, 0, 0))
+                                (330, 80, 128, 9, 1, 0), (530, 70, 256, 21, 0, 0), (530, 70, 256, 11, 1, 0), (200, 64, 96, 7, 0, 0), (332, 60, 64, 11, 1, 0))
 rot = int(sys.argv[1]) if len(sys.argv) > 1 else 0                     # start with another configuration (first-launch effects)
 cnt = int(sys.argv[2]) if len(sys.argv) > 2 else len(CONFIGS)           # only the first cnt configurations (initcheck is slow)
 for (W, H, D, B, prof, uni) in (CONFIGS[rot:] + CONFIGS[:rot])[:cnt]:
