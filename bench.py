@@ -731,7 +731,7 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
                     "stage_ms_per_step": stage,
                     "other_kernels": {"rect": {"ms": stage["rect"], "hbm_frac": 4.0 * W * H * nb / (stage["rect"] * 1e-3) / 1e9 / hbm_peak,
-                                               "binding_resource": "ALU pipe / issue slots (ncu: 65 % / 74 %), not HBM"},
+                                               "binding_resource": "issue slots / ALU pipe (ncu: 75 % / 57 %), not HBM"},
                                       "xsobel": {"ms": stage["xsbl"], "hbm_frac": 4.0 * W * H * nb / (stage["xsbl"] * 1e-3) / 1e9 / hbm_peak},
                                       **(aux or {})}}
         cpu = None
