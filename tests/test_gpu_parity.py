@@ -628,6 +628,28 @@ def test_opencv_postfilters(u, fe640, golden, cv_golden, oracle):
     fe640.set_bm_params(disp12_max_diff=-1, speckle_window_size=0, speckle_range=0)
 
 
+@pytest.mark.parametrize("D,B,cap", [(128, 31, 33), (128, 31, 34), (256, 31, 33), (128, 21, 63), (64, 31, 33)])
+def test_opencv_profile_column_sums_at_the_fp16_limit(u, oracle, D, B, cap):
+    """The cv::StereoBM variants with 16-bit staged rows keep their column sums as fp16 bit patterns (bm_fused.cuh), exact below 2048:
+    window x 2 cap = 2046 is the largest configuration that takes them (cap 34: 2108 falls back to byte rows).  Vertical stripes
+    of full contrast drive |x-Sobel| to the clip in every row, so whole columns of the cost volume sit at window x 2 cap."""
+    W, H = 448, 72
+    rng = np.random.default_rng(5)
+    cols = np.repeat(rng.integers(0, 2, W // 2 + 1), 2)[:W] * 255                 # stripes two pixels wide, random phase
+    L = np.broadcast_to(cols.astype(np.uint8), (H, W)).copy()
+    R = np.roll(255 - L, 3, axis=1)
+    L[::9, ::5] ^= 0x40; R[::7, ::3] ^= 0x20                                      # a little texture so that not every pixel is a tie
+    with u.StereoFrontEnd(0, W, H, 1) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_OPENCV, num_disparities=D, block_size=B, texture_threshold=0,
+                         uniqueness_ratio=3, prefilter_cap=cap, min_disparity=0, disp12_max_diff=-1, speckle_window_size=0)
+        fe.submit_rect(0, L[None], R[None])
+        b = fe.wait()
+        got = fe.receive_disp(b)[0]; xl, xr = fe.receive_xsbl(b)
+    assert int(np.abs(xl[0].astype(int) - xr[0].astype(int)).max()) == 2 * cap      # the clip is reached
+    want = oracle.bm_cv(xl[0], xr[0], wsz=B, ndisp=D, prefilter_cap=cap, texture_threshold=0, uniqueness_ratio=3)
+    assert np.array_equal(got, want), int((got != want).sum())
+
+
 @pytest.mark.parametrize("W,H", [(332, 70), (330, 64), (648, 50), (2056, 40)])
 def test_opencv_postfilters_ragged_widths(u, oracle, W, H):
     """validateDisparity + filterSpeckles on widths that take the other code paths of postfilter.cu: a multiple of 4 but not of 8 (scalar
