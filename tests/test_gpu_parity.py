@@ -628,6 +628,29 @@ def test_opencv_postfilters(u, fe640, golden, cv_golden, oracle):
     fe640.set_bm_params(disp12_max_diff=-1, speckle_window_size=0, speckle_range=0)
 
 
+@pytest.mark.parametrize("W,H,D,B,n", [(640, 150, 64, 21, 1), (523, 101, 64, 17, 5), (640, 90, 64, 31, 8), (700, 133, 128, 21, 2),
+                                        (640, 84, 64, 21, 3), (640, 83, 64, 21, 3)])
+def test_saturating_chain_in_y_bands(u, oracle, W, H, D, B, n):
+    """A handful of pairs with the 10-bit saturating column sums (bm_calc_sad.v:449-466): the chain over the image height is cut into
+    16-row bands -- band functions (chain from 0, chain from 1023, sum of n - o), k_bm_chain, bands from their exact start states
+    (bm_fused.cuh).  Every frame == oracle on frames that saturate and recover (stripes of full contrast in the middle third, so the
+    deficit of a clipped sum has to be carried across band boundaries); heights around the 64-row threshold take both paths."""
+    L, R = u.synth_batch(31, 0, n, W, H, D)
+    L[:, H // 3: 2 * H // 3] = np.where(L[:, H // 3: 2 * H // 3] > 127, 255, 0).astype(np.uint8)
+    with u.StereoFrontEnd(0, W, H, n) as fe:
+        fe.set_bm_params(width=W, height=H, profile=u.PROFILE_RTL, block_size=B, num_disparities=D, x_store_offset=1, uni_enable=0)
+        for bank in (0, 1, 0):                                        # the scratch of both banks, and its reuse
+            fe.submit_rect(bank, L, R)
+            b = fe.wait()
+            d = fe.receive_disp(b); xl, xr = fe.receive_xsbl(b)
+    sat = 0
+    for i in range(n):
+        want = oracle.bm_rtl(xl[i], xr[i], wsz=B, ndisp=D)
+        sat += oracle.sat_events()
+        assert np.array_equal(d[i], want), f"frame {i}: {int((d[i] != want).sum())} pixels"
+    assert sat > 0
+
+
 @pytest.mark.parametrize("D,B,cap", [(128, 31, 33), (128, 31, 34), (256, 31, 33), (128, 21, 63), (64, 31, 33)])
 def test_opencv_profile_column_sums_at_the_fp16_limit(u, oracle, D, B, cap):
     """The cv::StereoBM variants with 16-bit staged rows keep their column sums as fp16 bit patterns (bm_fused.cuh), exact below 2048:

@@ -431,7 +431,10 @@ int launch_bm_fast(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame
     //  ~480 sequential rows; there the V/H-role kernel's row is 15 % shorter -- single pair 0.46 ms against 0.54 ms)
     static const int fused_env = getenv("U96_BM_FUSED") ? atoi(getenv("U96_BM_FUSED")) : -1;
     const bool few_sat64 = fused_env != 1 && c.profile == U96_PROFILE_RTL && c.D == 64 && c.wsz * 63 > 1023 && n <= 18;
-    if (bm_takes_fused(c) && !few_sat64) return launch_bm_fused_rtl(xl, xr, pitch, frame, disp, c, n, s);
+    // ... unless the chain can be cut into y-bands (bm_fused.cuh: band functions, <= 8 pairs, scratch provided by the caller)
+    const size_t band_need = bm_sat_scratch_bytes(c, n);
+    const bool banded = fused_env != 0 && band_need > 0 && c.sat_scratch && c.sat_scratch_bytes >= band_need;
+    if (bm_takes_fused(c) && (banded || !few_sat64)) return launch_bm_fused_rtl(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 64) return launch_bm_fast_cs1(xl, xr, pitch, frame, disp, c, n, s);
     if (c.D == 128) return launch_bm_fast_cs2(xl, xr, pitch, frame, disp, c, n, s);
     return launch_bm_fast_cs4(xl, xr, pitch, frame, disp, c, n, s);

@@ -75,6 +75,14 @@ __device__ __forceinline__ uint32_t satsub_absdiff_u16x2(uint32_t c, uint32_t l,
     return d;
 }
 
+// |l - r| on two u16 lanes below 2048 as an integer bit pattern, on the FMA pipe; and max(c - m, 0) for such a pattern m
+__device__ __forceinline__ uint32_t absdiff_f16_u16x2(uint32_t l, uint32_t r)
+{
+    uint32_t d;
+    asm("{\n\t.reg .b32 t;\n\tsub.f16x2 t, %1, %2;\n\tabs.f16x2 %0, t;\n\t}" : "=r"(d) : "r"(l), "r"(r));
+    return d;
+}
+
 // bytes (i+1)..(i+8) of the 16-byte pair (a, b): the R window of column i of a segment (i = 7: b itself)
 __device__ __forceinline__ uint2 r_window(uint2 a, uint2 b, int i)
 {
@@ -91,11 +99,22 @@ __device__ __forceinline__ uint2 r_window(uint2 a, uint2 b, int i)
 // resident CTAs per SM: 64 disparities 4 (54.5 KB, 72 registers), 128: 2, 256: 1
 __host__ __device__ constexpr int fused_occupancy(int ng) { return ng == 8 ? 4 : ng == 16 ? 2 : 1; }
 
-template <int PROFILE, bool SAT, int NG, bool WD>
-__global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fused(const FastArgs a)
+// The saturating chain in y-bands (a handful of pairs: the sweep over the image height is a latency problem, single pair 0.46 ms).
+// One row of the chain is f(c) = min(max(c - o, 0) + n, 1023) (bm_calc_sad.v:449-466): a clamp-add map c -> min(max(c + a, lo), hi).
+// Such maps are closed under composition -- (a2, lo2, hi2) o (a1, lo1, hi1) = (a1 + a2, f2(lo1), f2(hi1)) -- so the effect of a whole
+// band of rows on ANY start state is three numbers per column sum: the chain run from 0, the chain run from 1023, and the plain sum of
+// n - o.  MODE 1 of the kernel computes those for every band in parallel (column-sum step only), k_bm_chain applies them band after
+// band (one clamp-add per band and column sum) and MODE 0 then runs every band in parallel from its exact start state.  Bit-exact by
+// construction; three times the arithmetic, but spread over the whole GPU instead of four SMs.
+__host__ __device__ constexpr size_t fused_state_block(int ng) { return (size_t)U_NC * ng + 2 * U_NSEG; }     // uint4 per (frame, band, tile): column sums + guard lanes
+
+template <int PROFILE, bool SAT, int NG, bool WD, int MODE = 0>
+__global__ void __launch_bounds__(U_NSEG * NG + 64, MODE == 1 ? 1 : fused_occupancy(NG)) k_bm_fused(const FastArgs a)
 {
+    constexpr bool COMPOSE = (MODE == 1);
     constexpr bool CV = (PROFILE == U96_PROFILE_OPENCV);
     constexpr bool WIDE = U96_FUSED_WIDE && WD;                  // RTL: always; OPENCV: when window x 2 cap < 2048 (column sums exact as fp16)
+    static_assert(!COMPOSE || (WIDE && SAT && PROFILE == U96_PROFILE_RTL), "band functions exist for the saturating RTL chain only");
     constexpr bool KEEP = FusedSmem<NG, WIDE, SAT, CV>::KEEP;
     // same-box A/B (profiles/r02_summary.md): the 72-register variants without the wide rows lose 4 % to a two-pixel look-ahead
     constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? (WIDE ? 2 : 0) : (NG == 16) ? 2 : 1;
@@ -119,6 +138,14 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
     const uint8_t *gr = a.xr + (size_t)f * a.frame;
     int16_t *gout = a.disp + (size_t)f * a.dframe;
     const int pw = a.pitch >> 2;
+    // bands that carry the saturating chain: band > 0 starts behind its window fill, from the state k_bm_chain left for it
+    // (MODE 0 = the plain kernel, 1 = band functions, 2 = bands from their start states: the plain kernel carries none of this)
+    constexpr bool carry = (MODE != 0);
+    const int it0 = (carry && band > 0) ? wsz - 1 : 0;
+    const int gofs = carry ? band * a.band_h : 0;                // rows fed before this band's iteration 0 (is the oldest row part of the window?)
+    constexpr size_t SBLK = fused_state_block(NG);
+    uint4 *fn_blk = COMPOSE ? a.st_fn + (((size_t)f * (a.nbands - 1) + band) * a.ntx_tiles + tile) * 3 * SBLK : nullptr;
+    const uint4 *sv_blk = (MODE == 2 && band > 0) ? a.st_val + (((size_t)f * a.nbands + band) * a.ntx_tiles + tile) * SBLK : nullptr;
 
     if (warp < CW) {
         // ======================================================================================
@@ -126,8 +153,13 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
         // ======================================================================================
         const int s = tid >> LG, g = tid & (NG - 1);
         uint4 c[8];                                                   // column sums: c[i] = column 8s+i, slots k <-> d = 8g+7-k
+        uint4 ch[COMPOSE ? 8 : 1], ac[COMPOSE ? 8 : 1];               // MODE 1: the chain from 1023 and the sum of n - o (c is the chain from 0)
 #pragma unroll
-        for (int i = 0; i < 8; i++) c[i] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 8; i++) c[i] = sv_blk ? sv_blk[(size_t)(8 * s + i) * NG + g] : make_uint4(0, 0, 0, 0);
+        if (COMPOSE) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { ch[i] = make_uint4(0x03FF03FFu, 0x03FF03FFu, 0x03FF03FFu, 0x03FF03FFu); ac[i] = make_uint4(0, 0, 0, 0); }
+        }
         const int aoff = 8 * (s - g) + D;                             // rrow index of word A (word B = +8)
         const int two_h = 2 * h;
         const int q0 = two_h >> 3;                                    // blocks fully inside the window of the segment's first pixel: s+1 .. s+q0-1
@@ -139,7 +171,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
         const int px = 32 * warp + lane;
         const int out_x = ctr0 + px + (CV ? 0 : a.x_store_offset);
         const bool px_ok = (warp < 5) && (px < ntx) && (out_x < a.W);          // (the RTL's store offset can push the last pixel of a row out of the image)
-        int16_t *out_p = gout + (ptrdiff_t)(yb0 - (wsz - 1)) * (ptrdiff_t)a.dpitch + out_x;   // row of iteration 0 (not dereferenced before wsz-1)
+        int16_t *out_p = gout + (ptrdiff_t)(yb0 - (wsz - 1) + it0) * (ptrdiff_t)a.dpitch + out_x;   // row of iteration it0 (not dereferenced before wsz-1)
 
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");        // rows of iteration 0 are staged
         uint4 pf_e0, pf_e1, pf_la, pf_lb;                             // WIDE: oldest-row operands of the coming iteration
@@ -148,12 +180,54 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             pf_e0 = E[0]; pf_e1 = E[1];
             pf_la = *reinterpret_cast<const uint4 *>(&sm.lrow4[bb][1][8 * s]); pf_lb = *reinterpret_cast<const uint4 *>(&sm.lrow4[bb][1][8 * s + 4]);
         };
-        if (WIDE) prefetch_old(0);
-        for (int it = 0; it < nsteps; it++) {
+        if (WIDE) prefetch_old(it0 & 1);
+        for (int it = it0; it < nsteps; it++) {
             const int b = it & 1;
             uint4 run;                                                // prefix sums of the 8 columns; after phase 1: the block sum
             // ---- phase 1: the newest and the oldest row enter the 64 column sums of this thread ----
-            if constexpr (WIDE) {
+            if constexpr (COMPOSE) {
+                // the same two rows enter the chain from 0, the chain from 1023 and the sum of n - o; no window sums in this mode
+                {
+                    const uint4 e0 = pf_e0, e1 = pf_e1, la = pf_la, lb = pf_lb;
+                    const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    uint32_t ow[7];
+#pragma unroll
+                    for (int k = 0; k < 7; k++) ow[k] = __funnelshift_r(ew[k], ew[k + 1], 16);
+                    const uint32_t lw[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t *w = (i & 1) ? &ew[(i + 1) >> 1] : &ow[i >> 1];
+                        const uint32_t m0 = absdiff_f16_u16x2(lw[i], w[0]), m1 = absdiff_f16_u16x2(lw[i], w[1]);
+                        const uint32_t m2 = absdiff_f16_u16x2(lw[i], w[2]), m3 = absdiff_f16_u16x2(lw[i], w[3]);
+                        c[i].x = satsub_u16x2(c[i].x, m0); c[i].y = satsub_u16x2(c[i].y, m1); c[i].z = satsub_u16x2(c[i].z, m2); c[i].w = satsub_u16x2(c[i].w, m3);
+                        ch[i].x = satsub_u16x2(ch[i].x, m0); ch[i].y = satsub_u16x2(ch[i].y, m1); ch[i].z = satsub_u16x2(ch[i].z, m2); ch[i].w = satsub_u16x2(ch[i].w, m3);
+                        ac[i].x = __vsub2(ac[i].x, m0); ac[i].y = __vsub2(ac[i].y, m1); ac[i].z = __vsub2(ac[i].z, m2); ac[i].w = __vsub2(ac[i].w, m3);
+                    }
+                }
+                {
+                    const uint4 *E = reinterpret_cast<const uint4 *>(&sm.rrow[b][0][2 * aoff]);
+                    const uint4 e0 = E[0], e1 = E[1];
+                    const uint4 la = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][0][8 * s]), lb = *reinterpret_cast<const uint4 *>(&sm.lrow4[b][0][8 * s + 4]);
+                    const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    uint32_t ow[7];
+#pragma unroll
+                    for (int k = 0; k < 7; k++) ow[k] = __funnelshift_r(ew[k], ew[k + 1], 16);
+                    const uint32_t lw[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t *w = (i & 1) ? &ew[(i + 1) >> 1] : &ow[i >> 1];
+                        const uint32_t n0 = __vabsdiffu4(lw[i], w[0]), n1 = __vabsdiffu4(lw[i], w[1]), n2 = __vabsdiffu4(lw[i], w[2]), n3 = __vabsdiffu4(lw[i], w[3]);
+                        c[i].x = __viaddmin_u16x2(c[i].x, n0, 0x03FF03FFu); c[i].y = __viaddmin_u16x2(c[i].y, n1, 0x03FF03FFu);
+                        c[i].z = __viaddmin_u16x2(c[i].z, n2, 0x03FF03FFu); c[i].w = __viaddmin_u16x2(c[i].w, n3, 0x03FF03FFu);
+                        ch[i].x = __viaddmin_u16x2(ch[i].x, n0, 0x03FF03FFu); ch[i].y = __viaddmin_u16x2(ch[i].y, n1, 0x03FF03FFu);
+                        ch[i].z = __viaddmin_u16x2(ch[i].z, n2, 0x03FF03FFu); ch[i].w = __viaddmin_u16x2(ch[i].w, n3, 0x03FF03FFu);
+                        ac[i].x = __vadd2(ac[i].x, n0); ac[i].y = __vadd2(ac[i].y, n1); ac[i].z = __vadd2(ac[i].z, n2); ac[i].w = __vadd2(ac[i].w, n3);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+                prefetch_old(b ^ 1);
+                continue;
+            } else if constexpr (WIDE) {
                 // oldest row first, on the FMA pipe: c = max(c - |l - r|, 0); then the newest row: c = min(c + |l - r|, 1023) on the ALU pipe
                 // (exact sums, window <= 16: the same without the ceiling -- the subtraction never clamps and the add is a plain one)
                 uint4 *prow = &sm.pre[8 * s][g];
@@ -367,6 +441,13 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             // next one): their loads are in flight across the back edge instead of at the head of the column-sum step
             if (WIDE) prefetch_old(b ^ 1);
         }
+        if (COMPOSE) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const size_t e = (size_t)(8 * s + i) * NG + g;
+                fn_blk[e] = c[i]; fn_blk[SBLK + e] = ch[i]; fn_blk[2 * SBLK + e] = ac[i];
+            }
+        }
     } else if (warp == CW) {
         // ======================================================================================
         // staging role: rows of iteration it+1 (newest, oldest) -> shared memory as they are (RTL: 6-bit masked, lr_din, bm_calc_sad.v:82-101)
@@ -385,13 +466,13 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             const int w0 = (x0 - (x0 & 3)) >> 2;
             m[j] = (x0 & 3) * 8;
             ok0[j] = on[j] && w0 >= 0 && w0 < pw; ok1[j] = on[j] && w0 + 1 >= 0 && w0 + 1 < pw;
-            p[j] = reinterpret_cast<const uint32_t *>(isr ? gr : gl) + ((ptrdiff_t)(yb0 - h - (rt[j] ? wsz : 0)) * pw + w0);
+            p[j] = reinterpret_cast<const uint32_t *>(isr ? gr : gl) + ((ptrdiff_t)(yb0 - h - (rt[j] ? wsz : 0) + it0) * pw + w0);
             so[j] = (uint32_t)((isr ? offsetof(SM, rrow) + (size_t)rt[j] * RB + (WIDE ? 8 : 4) * q : offsetof(SM, lrow4) + (size_t)rt[j] * 4 * U_NC + 16 * q));
 
         }
         uint32_t w0r[NI], w1r[NI];
         auto load = [&](int it) {
-            const bool live_n = it < nsteps, live_o = live_n && it >= wsz;
+            const bool live_n = it < nsteps, live_o = live_n && it + gofs >= wsz;
 #pragma unroll
             for (int j = 0; j < NI; j++) {
                 const bool live = rt[j] ? live_o : live_n;
@@ -421,9 +502,9 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                     }
                 }
         };
-        load(0); store(0);
+        load(it0); store(it0);
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-        for (int it = 0; it < nsteps; it++) {
+        for (int it = it0; it < nsteps; it++) {
             load(it + 1);
             store(it + 1);
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
@@ -434,10 +515,17 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
         // OPENCV: the texture column sums |L' - cap| (cv::StereoBM textureThreshold) and their prefix sums over the tile's columns.
         // ======================================================================================
         uint4 cg[2];                                                  // RTL: item = lane + 32*j: segment = item >> 1, which = item & 1
+        uint4 cgh[COMPOSE ? 2 : 1], cga[COMPOSE ? 2 : 1];
         cg[0] = cg[1] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int item = lane + 32 * j;
+            if (sv_blk && item < 2 * U_NSEG) cg[j] = sv_blk[(size_t)U_NC * NG + (item & 1) * U_NSEG + (item >> 1)];
+            if (COMPOSE) { cgh[j] = make_uint4(0x03FF03FFu, 0x03FF03FFu, 0x03FF03FFu, 0x03FF03FFu); cga[j] = make_uint4(0, 0, 0, 0); }
+        }
         const uint32_t cap4 = (uint32_t)a.cap * 0x01010101u;
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-        for (int it = 0; it < nsteps; it++) {
+        for (int it = it0; it < nsteps; it++) {
             const int b = it & 1;
             if (CV) {
                 // lane = segment (20 of 32 lanes): 8 columns packed as 4 x u16x2
@@ -447,7 +535,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                 const uint32_t an0 = __vabsdiffu4(ln.x, cap4), an1 = __vabsdiffu4(ln.y, cap4);
                 uint4 &cc = cg[0];
                 cc.x += fprmt(an0, 0, 0x4140); cc.y += fprmt(an0, 0, 0x4342); cc.z += fprmt(an1, 0, 0x4140); cc.w += fprmt(an1, 0, 0x4342);
-                if (it >= wsz) {                                      // (before that the oldest row is not part of the window: its staged zeros are not pixels)
+                if (it + gofs >= wsz) {                               // (before that the oldest row is not part of the window: its staged zeros are not pixels)
                     const uint32_t ao0 = __vabsdiffu4(lo.x, cap4), ao1 = __vabsdiffu4(lo.y, cap4);
                     cc.x -= fprmt(ao0, 0, 0x4140); cc.y -= fprmt(ao0, 0, 0x4342); cc.z -= fprmt(ao1, 0, 0x4140); cc.w -= fprmt(ao1, 0, 0x4342);
                 }
@@ -484,6 +572,13 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                                 rold = make_uint4(__funnelshift_r(rold.x, rold.y, 16), __funnelshift_r(rold.y, rold.z, 16), __funnelshift_r(rold.z, rold.w, 16), __funnelshift_r(rold.w, to, 16));
                             }
                             // columns (i, i+1) of the pair: low half of word i, high half of word i+1
+                            if constexpr (COMPOSE) {
+                                const uint32_t m0 = absdiff_f16_u16x2(fprmt(loa.x, loa.y, 0x7610), rold.x), m1 = absdiff_f16_u16x2(fprmt(loa.z, loa.w, 0x7610), rold.y);
+                                const uint32_t m2 = absdiff_f16_u16x2(fprmt(lob.x, lob.y, 0x7610), rold.z), m3 = absdiff_f16_u16x2(fprmt(lob.z, lob.w, 0x7610), rold.w);
+                                uint4 &hh = cgh[j], &aa = cga[j];
+                                hh.x = satsub_u16x2(hh.x, m0); hh.y = satsub_u16x2(hh.y, m1); hh.z = satsub_u16x2(hh.z, m2); hh.w = satsub_u16x2(hh.w, m3);
+                                aa.x = __vsub2(aa.x, m0); aa.y = __vsub2(aa.y, m1); aa.z = __vsub2(aa.z, m2); aa.w = __vsub2(aa.w, m3);
+                            }
                             cc.x = satsub_absdiff_u16x2(cc.x, fprmt(loa.x, loa.y, 0x7610), rold.x); cc.y = satsub_absdiff_u16x2(cc.y, fprmt(loa.z, loa.w, 0x7610), rold.y);
                             cc.z = satsub_absdiff_u16x2(cc.z, fprmt(lob.x, lob.y, 0x7610), rold.z); cc.w = satsub_absdiff_u16x2(cc.w, fprmt(lob.z, lob.w, 0x7610), rold.w);
                             const uint32_t n0 = __vabsdiffu4(fprmt(lna.x, lna.y, 0x7610), rn.x), n1 = __vabsdiffu4(fprmt(lna.z, lna.w, 0x7610), rn.y);
@@ -492,6 +587,12 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
                                 cc.x = __viaddmin_u16x2(cc.x, n0, 0x03FF03FFu); cc.y = __viaddmin_u16x2(cc.y, n1, 0x03FF03FFu);
                                 cc.z = __viaddmin_u16x2(cc.z, n2, 0x03FF03FFu); cc.w = __viaddmin_u16x2(cc.w, n3, 0x03FF03FFu);
                             } else { cc.x += n0; cc.y += n1; cc.z += n2; cc.w += n3; }
+                            if constexpr (COMPOSE) {
+                                uint4 &hh = cgh[j], &aa = cga[j];
+                                hh.x = __viaddmin_u16x2(hh.x, n0, 0x03FF03FFu); hh.y = __viaddmin_u16x2(hh.y, n1, 0x03FF03FFu);
+                                hh.z = __viaddmin_u16x2(hh.z, n2, 0x03FF03FFu); hh.w = __viaddmin_u16x2(hh.w, n3, 0x03FF03FFu);
+                                aa.x = __vadd2(aa.x, n0); aa.y = __vadd2(aa.y, n1); aa.z = __vadd2(aa.z, n2); aa.w = __vadd2(aa.w, n3);
+                            }
                             *reinterpret_cast<uint4 *>(gd + 8 * s) = cc;
                         } else {
                         uint2 rv[2];
@@ -524,15 +625,74 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, fused_occupancy(NG)) k_bm_fu
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         }
+        if (COMPOSE) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int item = lane + 32 * j;
+                if (item < 2 * U_NSEG) {
+                    const size_t e = (size_t)U_NC * NG + (item & 1) * U_NSEG + (item >> 1);
+                    fn_blk[e] = cg[j]; fn_blk[SBLK + e] = cgh[j]; fn_blk[2 * SBLK + e] = cga[j];
+                }
+            }
+        }
     }
 }
 
-template <int PROFILE, bool SAT, int NG, bool WD>
+// Band start states of the saturating chain: state(b + 1) = min(max(state(b) + a_b, lo_b), hi_b), state(0) = 0, per u16 lane.
+// One thread = one uint4 (8 lanes) of one (frame, tile); nb - 1 sequential steps.
+__global__ void __launch_bounds__(256) k_bm_chain(const uint4 *__restrict__ fn, uint4 *__restrict__ st, int nb, int ntiles, size_t blk, int n)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile = blockIdx.y, f = blockIdx.z;
+    if (e >= blk) return;
+    auto step = [](uint32_t s, uint32_t a, uint32_t lo, uint32_t hi) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v = (int)((s >> (16 * k)) & 0xFFFFu) + (int)(int16_t)((a >> (16 * k)) & 0xFFFFu);
+            const int l = (int)((lo >> (16 * k)) & 0xFFFFu), h = (int)((hi >> (16 * k)) & 0xFFFFu);
+            r |= (uint32_t)min(max(v, l), h) << (16 * k);
+        }
+        return r;
+    };
+    uint4 s = make_uint4(0, 0, 0, 0);
+    for (int b = 0; b + 1 < nb; b++) {
+        const uint4 *fb = fn + (((size_t)f * (nb - 1) + b) * ntiles + tile) * 3 * blk;
+        const uint4 lo = fb[e], hi = fb[blk + e], a = fb[2 * blk + e];
+        s = make_uint4(step(s.x, a.x, lo.x, hi.x), step(s.y, a.y, lo.y, hi.y), step(s.z, a.z, lo.z, hi.z), step(s.w, a.w, lo.w, hi.w));
+        st[(((size_t)f * nb + b + 1) * ntiles + tile) * blk + e] = s;
+    }
+}
+
+template <int PROFILE, bool SAT, int NG, bool WD, int MODE = 0>
 static inline void fused_go(const FastArgs &a, int n, cudaStream_t s)
 {
     const int smem = (int)sizeof(FusedSmem<NG, U96_FUSED_WIDE && WD, SAT, PROFILE == U96_PROFILE_OPENCV>);
-    cudaFuncSetAttribute(k_bm_fused<PROFILE, SAT, NG, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_bm_fused<PROFILE, SAT, NG, WD><<<dim3(a.ntx_tiles, a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
+    cudaFuncSetAttribute(k_bm_fused<PROFILE, SAT, NG, WD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_bm_fused<PROFILE, SAT, NG, WD, MODE><<<dim3(a.ntx_tiles, MODE == 1 ? a.nbands - 1 : a.nbands, n), U_NSEG * NG + 64, smem, s>>>(a);
+}
+
+// y-bands of the saturating chain (64 / 128 disparities, a handful of pairs): rows per band, or 0 when the chain stays sequential
+constexpr int FUSED_BAND_MAX_PAIRS = 8;
+static inline int fused_band_rows() { static const int v = getenv("U96_SAT_BAND_ROWS") ? std::max(8, atoi(getenv("U96_SAT_BAND_ROWS"))) : 16; return v; }
+#define FUSED_BAND_ROWS fused_band_rows()
+static inline int fused_sat_bands(const BmConfig &c, int n, int *ntiles = nullptr)
+{
+    static const int env = getenv("U96_SAT_BANDS") ? atoi(getenv("U96_SAT_BANDS")) : 1;      // developer switch
+    if (!env || c.profile != U96_PROFILE_RTL || c.uni_enable || c.wsz * 63 <= 1023 || !(c.D == 64 || c.D == 128) || n > FUSED_BAND_MAX_PAIRS) return 0;
+    const int h = c.wsz >> 1, rows = c.H - 2 * h, ncen = (c.W - 2 - h) - (c.D + h) + 1, tx = U_NC - 2 * h;
+    if (rows < 4 * FUSED_BAND_ROWS || ncen <= 0) return 0;
+    const int tiles = (ncen + tx - 1) / tx;
+    if ((long long)n * tiles * fused_occupancy(c.D / 8) > fast_sm_count()) return 0;             // the sequential sweep already fills the SMs
+    if (ntiles) *ntiles = tiles;
+    return (rows + FUSED_BAND_ROWS - 1) / FUSED_BAND_ROWS;
+}
+static inline size_t fused_sat_scratch_bytes(const BmConfig &c, int n)
+{
+    int tiles = 0;
+    const int nb = fused_sat_bands(c, n, &tiles);
+    if (!nb) return 0;
+    return (size_t)n * tiles * fused_state_block(c.D / 8) * sizeof(uint4) * ((size_t)3 * (nb - 1) + nb);
 }
 
 // 64 / 128 / 256 disparities, window 9..31; RTL profile with the uniqueness filter off, or the cv::StereoBM profile
@@ -564,6 +724,18 @@ static inline int launch_bm_fused(const uint8_t *xl, const uint8_t *xr, int pitc
     }
     const bool sat = c.wsz * 63 > 1023;
     if (sat && a.TX > 144) return 0;                                             // cannot happen (window >= 17): FusedSmem::NPX
+    const int nb = fused_sat_bands(c, n);
+    if (nb && c.sat_scratch && c.sat_scratch_bytes >= fused_sat_scratch_bytes(c, n)) {
+        // band functions (all bands at once) -> band start states (sequential over the bands, one clamp-add each) -> every band at once
+        const size_t blk = fused_state_block(ng);
+        a.band_h = FUSED_BAND_ROWS; a.nbands = nb; a.st_mode = 1;
+        a.st_fn = reinterpret_cast<uint4 *>(c.sat_scratch);
+        a.st_val = a.st_fn + (size_t)n * (nb - 1) * a.ntx_tiles * 3 * blk;
+        if (ng == 8) fused_go<R, true, 8, true, 1>(a, n, s); else fused_go<R, true, 16, true, 1>(a, n, s);
+        k_bm_chain<<<dim3((unsigned)((blk + 255) / 256), a.ntx_tiles, n), 256, 0, s>>>(a.st_fn, a.st_val, nb, a.ntx_tiles, blk, n);
+        if (ng == 8) fused_go<R, true, 8, true, 2>(a, n, s); else fused_go<R, true, 16, true, 2>(a, n, s);
+        return 3;
+    }
     if (ng == 8)       { if (sat) fused_go<R, true, 8, true>(a, n, s);  else fused_go<R, false, 8, true>(a, n, s); }
     else if (ng == 16) { if (sat) fused_go<R, true, 16, true>(a, n, s); else fused_go<R, false, 16, true>(a, n, s); }
     else               { if (sat) fused_go<R, true, 32, true>(a, n, s); else fused_go<R, false, 32, true>(a, n, s); }

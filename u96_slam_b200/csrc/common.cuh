@@ -39,7 +39,9 @@ struct BmConfig {
     int uni_enable, uni_mode, uni_thr, x_store_offset, rtl_extended;   // RTL
     int cap, tex_thr, uniq;                                            // OPENCV
     int16_t *cost = nullptr;                                           // OPENCV: winning SAD per valid pixel (same pitch as disp) or null
+    void *sat_scratch = nullptr; size_t sat_scratch_bytes = 0;        // RTL, a handful of pairs: band functions / states of the saturating chain
 };
+size_t bm_sat_scratch_bytes(const BmConfig &c, int n);                 // scratch launch_bm wants for n pairs of this configuration (0: none)
 int  bm_smem_bytes(const BmConfig &c);
 int  bm_wave_frames(const BmConfig &c);
 int launch_bm(const uint8_t *xl, const uint8_t *xr, int pitch, size_t frame, Img16 disp,

@@ -60,6 +60,7 @@ struct Bank {
     int16_t *cost = nullptr;            // OPENCV post filters: winning SAD per pixel (lazy)
     int *cc = nullptr;                  // filterSpeckles: label + size, 2 int32 per pixel of a batch (lazy, per bank)
     size_t cc_cap = 0;
+    void *sat = nullptr; size_t sat_cap = 0;               // band functions / states of the saturating chain (a handful of pairs, bm_fused.cuh)
     uint8_t *stage = nullptr;           // tight staging area for host transfers of non-pitch-aligned widths (lazy): L | R | 16-bit out
     size_t stage_cap = 0;
     uint16_t *eig = nullptr;            // GFTT min-eigenvalue map (lazy), same pitch (in elements) as the u8 images
@@ -231,6 +232,7 @@ void u96_destroy(u96_handle *h)
         cudaFree(k.stage);
         cudaFree(k.cost);
         cudaFree(k.cc);
+        cudaFree(k.sat);
         cudaFree(k.eig);
         cudaFree(k.eig_max);
         if (k.done) cudaEventDestroy(k.done);
@@ -370,6 +372,14 @@ static int ensure_bank_buffers(u96_handle *h, Bank &k, int from, int n, bool hos
             k.cc_cap = need;
         }
     }
+    {
+        const size_t need = bm_sat_scratch_bytes(bm_config(h->bm), n);
+        if (need > k.sat_cap) {                               // the bank is idle here (not pending)
+            cudaFree(k.sat); k.sat = nullptr; k.sat_cap = 0;
+            if (cudaMalloc(&k.sat, need) != cudaSuccess) return U96_ERR_NOMEM;
+            k.sat_cap = need;
+        }
+    }
     if (h->gftt && from <= FROM_RECT && !k.eig)
         if (cudaMalloc(&k.eig, (size_t)pitch * h->maxH * h->maxB * sizeof(uint16_t)) != cudaSuccess ||
             cudaMalloc(&k.eig_max, (size_t)h->maxB * sizeof(uint32_t)) != cudaSuccess) return U96_ERR_NOMEM;
@@ -417,6 +427,7 @@ static int run_range(u96_handle *h, Bank &k, int from, int f0, int nf, cudaStrea
     const bool want_validate = cv && h->bm.disp12_max_diff >= 0;
     const bool want_speckle = cv && h->bm.speckle_window_size > 0 && h->bm.speckle_range >= 0;
     if (want_validate) cfg.cost = k.cost + o;
+    cfg.sat_scratch = k.sat; cfg.sat_scratch_bytes = k.sat_cap;
     h->launches += launch_bm(k.cur_xsbl[0] + (size_t)f0 * k.xsbl_frame, k.cur_xsbl[1] + (size_t)f0 * k.xsbl_frame, k.xsbl_pitch,
                              k.xsbl_frame, disp, cfg, nf, s);
     if (prof) CK(cudaEventRecord(k.ev[5], s));
