@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, MODE == 1 ? 1 : fused_occupa
     static_assert(!COMPOSE || (WIDE && SAT && PROFILE == U96_PROFILE_RTL), "band functions exist for the saturating RTL chain only");
     constexpr bool KEEP = FusedSmem<NG, WIDE, SAT, CV>::KEEP;
     // same-box A/B (profiles/r02_summary.md): the 72-register variants without the wide rows lose 4 % to a two-pixel look-ahead
-    constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? (WIDE ? 2 : 0) : (NG == 16) ? 2 : 1;
+    constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? (WIDE ? (SAT ? 1 : 2) : 0) : (NG == 16) ? 2 : 1;
     using SM = FusedSmem<NG, WIDE, SAT, CV>;
     constexpr int D = SM::D, RLEN = SM::RLEN, RB = SM::RB, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, MODE == 1 ? 1 : fused_occupa
         if (WIDE) prefetch_old(it0 & 1);
         for (int it = it0; it < nsteps; it++) {
             const int b = it & 1;
-            uint4 run;                                                // prefix sums of the 8 columns; after phase 1: the block sum
+            uint4 run = make_uint4(0, 0, 0, 0);                       // prefix sums of the 8 columns; after phase 1: the block sum
             // ---- phase 1: the newest and the oldest row enter the 64 column sums of this thread ----
             if constexpr (COMPOSE) {
                 // the same two rows enter the chain from 0, the chain from 1023 and the sum of n - o; no window sums in this mode
