@@ -723,7 +723,7 @@ def main():
                     "peak_source": "measured live: u96_microbench VABSDIFF4 issue rate (ALU pipe, 64 lanes/clk/SM); "
                                    "MEASURED_PEAKS.json has no integer figure",
                     "algorithmic_ops_per_launch": bmr["algorithmic_ops_per_launch"], "kernel_ms": bm_ms, "traffic": traffic, "traffic_note": traffic_note,
-                    "binding_resource": "no unit saturated (ncu: shared-memory data pipe 73 % of peak, issue slots 64 %, ALU pipe 54 %, FMA pipe 25 %): "
+                    "binding_resource": "no unit saturated (ncu: shared-memory data pipe 75 % of peak, issue slots 65 %, ALU pipe 54 %, FMA pipe 25 %): "
                                         "two CTA barriers per image row and dependent shared-memory loads leave 5 compute warps per scheduler "
                                         "latency bound (profiles/r02_summary.md)",
                     "hbm": {"achieved": 4.0 * W * H * nb / (bm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
