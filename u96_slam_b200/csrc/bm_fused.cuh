@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, MODE == 1 ? 1 : fused_occupa
     static_assert(!COMPOSE || (WIDE && SAT && PROFILE == U96_PROFILE_RTL), "band functions exist for the saturating RTL chain only");
     constexpr bool KEEP = FusedSmem<NG, WIDE, SAT, CV>::KEEP;
     // same-box A/B (profiles/r02_summary.md): the 72-register variants without the wide rows lose 4 % to a two-pixel look-ahead
-    constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? (WIDE ? (SAT ? 1 : 2) : 0) : (NG == 16) ? 2 : 1;
+    constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? ((WIDE && !CV) ? (SAT ? 1 : 2) : 0) : (NG == 16) ? 2 : 1;
     using SM = FusedSmem<NG, WIDE, SAT, CV>;
     constexpr int D = SM::D, RLEN = SM::RLEN, RB = SM::RB, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
@@ -717,7 +717,7 @@ static inline int launch_bm_fused(const uint8_t *xl, const uint8_t *xr, int pitc
         // (the reference's own configuration, main.cpp:198-212: cap 31, window 21)
         static const int cvw_env = getenv("U96_CV_WIDE") ? atoi(getenv("U96_CV_WIDE")) : 1;      // developer switch
         const bool wide = cvw_env && (c.wsz * 2 * c.cap < 2048);
-        if (ng == 8)       fused_go<V, false, 8, false>(a, n, s);   // (measured: at 72 registers the wide form spills and is 1 % slower here; +2.5 % / +11 % at 128 / 256)
+        if (ng == 8)       { if (wide) fused_go<V, false, 8, true>(a, n, s);  else fused_go<V, false, 8, false>(a, n, s); }   // (same-box A/B: -3.8 % / -2.5 % / -11 % at 64 / 128 / 256)
         else if (ng == 16) { if (wide) fused_go<V, false, 16, true>(a, n, s); else fused_go<V, false, 16, false>(a, n, s); }
         else               { if (wide) fused_go<V, false, 32, true>(a, n, s); else fused_go<V, false, 32, false>(a, n, s); }
         return 1;
