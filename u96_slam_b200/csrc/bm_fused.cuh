@@ -1,31 +1,35 @@
 // bm_fused.cuh -- SAD block matching with ONE compute role, sm_100a: 64 / 128 / 256 disparities, RTL profile with the uniqueness
 // filter off (the shipped register set, fpga.c:150-160) and the cv::StereoBM profile (texture, exact uniqueness, mirrored
-// sub-pixel neighbours).  Same arithmetic as bm_fast.cuh / bm.cu; different mapping.
+// sub-pixel neighbours).  Same arithmetic as bm_fast.cuh / bm.cu; different mapping.  This is the kernel that runs the headline
+// configuration (profiles/r02_summary.md).
 //
-// Why: ncu shows k_bm_fast bound by the shared-memory pipe (l1tex__data_pipe_lsu_wavefronts_mem_shared 77-80 % of peak, ALU pipe
-// 62 %): its V warps (thread = column) and H warps (lane = segment x disparity group) hold the column sums in two different
+// Why: ncu shows k_bm_fast bound by the shared-memory pipe (l1tex__data_pipe_lsu_wavefronts_mem_shared 77-85 % of peak, ALU pipe
+// 58-62 %): its V warps (thread = column) and H warps (lane = segment x disparity group) hold the column sums in two different
 // layouts, so every column sum crosses shared memory once as a store and twice as a load, on top of 16 byte-shifted R loads per
 // column; beyond 64 disparities the slices of a tile are separate CTAs of a cluster that exchange records through DSMEM.
 // Here ONE thread owns (segment of 8 columns) x (group of 8 disparities) for both steps, and a CTA holds ALL groups of its tile
 // (NG = 8 / 16 / 32 groups: 160 / 320 / 640 compute threads) -- no cluster, no record ring:
 //
 //   * the 64 running column sums of its 8x8 patch never leave the thread's registers (bm_calc_sad.v:449-466);
-//   * the R bytes of all 8 columns come from two aligned 8-byte words (the windows of neighbouring columns overlap by 7 bytes;
-//     each column's window is funnel-shifted out of them) -- no byte-shifted copies, the rows are staged as they are;
+//   * the R pixels of all 8 columns come from two aligned 16-byte loads (the windows of neighbouring columns overlap by 7 pixels):
+//     RTL variants and the cv::StereoBM variants whose column sums stay below 2048 stage the rows 16 bit per pixel ("WIDE": windows
+//     are words in the lane format of the sums, the oldest row runs on the FMA pipe as fp16), the others as bytes (funnel-shifted
+//     windows, PRMT widening) -- no byte-shifted copies in either form;
 //   * what crosses shared memory is the per-segment INCLUSIVE PREFIX SUM of the column sums (8 x 16 B per thread): the window sum
 //     of pixel p over columns [p, p+2h] is   own block sum - own prefix before p   (registers)
 //                                          + whole blocks in between                (their last prefix entry)
 //                                          + prefix entry of column p+2h            (one 16-byte load per pixel);
 //   * winner search on PACKED 16-bit minima (3 VIMNMX.U16x2 per 8 disparities instead of 8 key builds + 4 VIMNMX3); the exact
 //     "lowest disparity among the minima" (bm_calc_det.v strict <, bm_calc_upd.v strict < across dphases) is recovered once per
-//     pixel: a warp-local pass reduces the packed minima of 64 disparities to one key per (pixel, 64-disparity chunk), the thread
+//     pixel: a warp-local pass reduces the packed minima of 64 disparities to one key per (pixel, 64-disparity chunk), the lane
 //     that owns the pixel takes the smallest chunk key, rescans the winning group's eight sums, fetches the winner's neighbours,
-//     forms the sub-pixel fraction, formats and stores -- no record ring.
+//     forms the sub-pixel fraction, formats and stores -- no record ring;
+//   * a handful of pairs of the saturating chain run in y-bands from exact start states (MODE 1 / 2, k_bm_chain; see below).
 //
 // CTA = 5*NG/8 compute warps + 1 staging warp + 1 guard warp (disparities -1 and D: bm_calc_sad.v lanes 0 and 33 of the first and
 // last dphase, column-parallel).  Two barriers per image row: all warps after the column-sum step, the compute warps after the
-// window-sum step (the prefix buffer is single: four 64-disparity CTAs fit an SM).  ~700 shared-memory wavefronts per tile row and
-// 64 disparities against ~1010 of k_bm_fast.
+// window-sum step (the prefix buffer is single: four 64-disparity CTAs fit an SM).  ~810 shared-memory wavefronts per tile row and
+// 64 disparities against ~970 of k_bm_fast.
 #pragma once
 #include "bm_fast.cuh"
 
@@ -43,8 +47,8 @@ constexpr int U_NC = 160, U_NSEG = 20;                 // tile columns, segments
 #define U96_FUSED_WIDE 1                   // 0: the RTL variants use the byte rows + PRMT widening of the cv::StereoBM variants
 #endif
 
-// WIDE (the RTL variants: 6-bit pixels, column sums below 2048): the staged R rows are 16-bit per pixel, so the 8-disparity window of a column is four words
-// already in the 2 x u16 lane format of the column sums -- aligned words for the odd columns of a segment, and for the even ones
+// WIDE (the RTL variants: 6-bit pixels; cv::StereoBM variants with window x 2 cap < 2048: column sums below 2048): the staged R rows
+// are 16-bit per pixel, so the 8-disparity window of a column is four words already in the 2 x u16 lane format of the column sums -- aligned words for the odd columns of a segment, and for the even ones
 // seven 16-bit funnel shifts shared by all four of them: no PRMT widening (64 per row and thread) on the ALU pipe, which binds
 // this step, and the oldest row's |l - r| and saturating subtract run on the FMA pipe as fp16 (satsub_absdiff_u16x2).
 template <int NG, bool WIDE, bool SAT, bool CV>
@@ -55,7 +59,7 @@ struct FusedSmem {
     uint4 pre[U_NC + 8][NG];               // inclusive prefix sums inside a segment: [column][group] = 8 x u16; 8 never-written pad columns: the
                                            // unrolled sweep of the last segment reads up to 7 columns past the tile for pixels nobody finishes
     uint16_t sad[NPX][SADP];               // window sums of the row in flight; pitch 2D+16 B: rows skew over the banks
-    uint32_t pmin[NPS][PMS];            // packed minima [segment][pixel j][group] (odd | even disparities); 9*NG-word segment stride: the
+    uint32_t pmin[NPS][PMS];               // packed minima [segment][pixel j][group] (odd | even disparities); 9*NG-word segment stride: the
                                            // segments of a warp store to disjoint banks
     static constexpr bool KEEP = U96_FUSED_KEEP && NG == 8;      // winner key and group stay in registers: ckey is not used
     uint32_t ckey[KEEP ? 4 : NPX][CV ? 2 : 1];     // per pixel: winner key (min SAD << 8 | group code) and, OPENCV, the smallest group minimum outside the
@@ -99,12 +103,13 @@ __device__ __forceinline__ uint2 r_window(uint2 a, uint2 b, int i)
 // resident CTAs per SM: 64 disparities 4 (54.5 KB, 72 registers), 128: 2, 256: 1
 __host__ __device__ constexpr int fused_occupancy(int ng) { return ng == 8 ? 4 : ng == 16 ? 2 : 1; }
 
-// The saturating chain in y-bands (a handful of pairs: the sweep over the image height is a latency problem, single pair 0.46 ms).
+// The saturating chain in y-bands (a handful of pairs: the sweep over the image height is a latency problem, 0.41-0.46 ms however idle the GPU).
 // One row of the chain is f(c) = min(max(c - o, 0) + n, 1023) (bm_calc_sad.v:449-466): a clamp-add map c -> min(max(c + a, lo), hi).
 // Such maps are closed under composition -- (a2, lo2, hi2) o (a1, lo1, hi1) = (a1 + a2, f2(lo1), f2(hi1)) -- so the effect of a whole
 // band of rows on ANY start state is three numbers per column sum: the chain run from 0, the chain run from 1023, and the plain sum of
 // n - o.  MODE 1 of the kernel computes those for every band in parallel (column-sum step only), k_bm_chain applies them band after
-// band (one clamp-add per band and column sum) and MODE 0 then runs every band in parallel from its exact start state.  Bit-exact by
+// band (one clamp-add per band and column sum) and MODE 2 then runs every band in parallel from its exact start state (MODE 0: the
+// plain kernel).  Bit-exact by
 // construction; three times the arithmetic, but spread over the whole GPU instead of four SMs.
 __host__ __device__ constexpr size_t fused_state_block(int ng) { return (size_t)U_NC * ng + 2 * U_NSEG; }     // uint4 per (frame, band, tile): column sums + guard lanes
 
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(U_NSEG * NG + 64, MODE == 1 ? 1 : fused_occupa
     static_assert(!COMPOSE || (WIDE && SAT && PROFILE == U96_PROFILE_RTL), "band functions exist for the saturating RTL chain only");
     constexpr bool KEEP = FusedSmem<NG, WIDE, SAT, CV>::KEEP;
     // same-box A/B (profiles/r02_summary.md): the 72-register variants without the wide rows lose 4 % to a two-pixel look-ahead
-    constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? ((WIDE && !CV) ? (SAT ? 1 : 2) : 0) : (NG == 16) ? 2 : 1;
+    constexpr int PF = (U96_FUSED_PF >= 0) ? U96_FUSED_PF : (NG == 8) ? ((WIDE && !CV) ? (SAT ? 1 : 2) : 0) : (NG == 16) ? ((WIDE && CV) ? 0 : 2) : 1;
     using SM = FusedSmem<NG, WIDE, SAT, CV>;
     constexpr int D = SM::D, RLEN = SM::RLEN, RB = SM::RB, SADP = SM::SADP, NCH = SM::NCH;
     constexpr int NCT = U_NSEG * NG, CW = NCT / 32, NT = NCT + 64;    // compute threads / warps | + staging warp + guard warp
