@@ -12,14 +12,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 OBJDIR = os.path.join(PKG, "lib", "obj")
 
 
-def source_sha16():
-    """SHA-256 (first 16 hex digits) over the CUDA sources and the ABI header: identifies the code a profile was taken with.  (nvcc does
-    not produce bit-identical libraries from identical sources, so the hash of the .so would not survive a rebuild.)"""
+def source_sha16(prefix="bm"):
+    """SHA-256 (first 16 hex digits) over the sources of the BM kernels (csrc/bm*.cu, bm*.cuh, common.cuh): identifies the code a
+    BM profile was taken with.  (nvcc does not produce bit-identical libraries from identical sources, so the hash of the .so would
+    not survive a rebuild; the handle / rect / post-filter sources do not change what the BM kernel is.)"""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "u96_stereo.h")]:
+    for f in sorted(os.listdir(CSRC)):
         path = os.path.join(CSRC, f)
-        if os.path.isfile(path) and f.endswith((".cu", ".cuh", ".h")):
+        if os.path.isfile(path) and f.endswith((".cu", ".cuh")) and (f.startswith(prefix) or f == "common.cuh"):
             h.update(f.encode()); h.update(open(path, "rb").read())
     return h.hexdigest()[:16]
 

@@ -376,8 +376,8 @@ static int ensure_bank_buffers(u96_handle *h, Bank &k, int from, int n, bool hos
         const size_t need = bm_sat_scratch_bytes(bm_config(h->bm), n);
         if (need > k.sat_cap) {                               // the bank is idle here (not pending)
             cudaFree(k.sat); k.sat = nullptr; k.sat_cap = 0;
-            if (cudaMalloc(&k.sat, need) != cudaSuccess) return U96_ERR_NOMEM;
-            k.sat_cap = need;
+            if (cudaMalloc(&k.sat, need) == cudaSuccess) k.sat_cap = need;
+            else { k.sat = nullptr; cudaGetLastError(); }       // no scratch: the chain of this batch simply stays sequential (launch_bm checks)
         }
     }
     if (h->gftt && from <= FROM_RECT && !k.eig)
