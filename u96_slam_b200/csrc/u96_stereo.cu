@@ -505,7 +505,9 @@ static int submit_common(u96_handle *h, int bank, int from, const uint8_t *L, co
     if (!upload_only) { const int rc = ensure_border(h, k, s); if (rc != U96_OK) return abort_submit(h, k, s, rc); }
     const bool prof = h->profiling && !upload_only;
     if (prof) CKA(cudaEventRecord(k.ev[0], s));
-    const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= 64 && !upload_only;
+    static const int pipe_min_env = getenv("U96_PIPE_MIN") ? atoi(getenv("U96_PIPE_MIN")) : 0;        // developer override (frames)
+    const int pipe_min = pipe_min_env > 0 ? pipe_min_env : 64;
+    const bool pipelined = !device_src && !h->use_user_stream && !h->profiling && n >= pipe_min && !upload_only;
     k.staged = pipelined;
     if (!pipelined) {
         if (!zero_copy)
